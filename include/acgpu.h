@@ -1,0 +1,134 @@
+/*
+ * include/acgpu.h -- entry points that libacgpu ADDS to the aclib interface.
+ *
+ * The reference has no equivalent of these: aclib processes one host frame (or one line) per call
+ * (aclib/imgconvert.c:34-64, aclib/rescale.c:23-32, aclib/average.c:22-26).  A GPU needs many
+ * frames per launch and data that stays in HBM, so libacgpu offers
+ *   - batched, device-resident forms of ac_imgconvert / ac_rescale / ac_average, and
+ *   - frame-granular forms of their direct libtcvideo callers, tcv_deinterlace
+ *     (libtcvideo/tcvideo.c:290-389) and tcv_resize (libtcvideo/tcvideo.c:427-531),
+ *   - the small amount of device plumbing a C caller needs (device selection, memory, streams, events).
+ * Plain C ABI: pointers, sizes and opaque handles only.
+ *
+ * Conventions: functions returning int give 1 on success and 0 on failure (aclib's convention,
+ * aclib/ac.h:56-57); acgpu_last_error() then describes the failure for the calling thread.
+ * Every call acts on the calling thread's current device (acgpu_set_device; default 0, or
+ * $ACGPU_DEVICE).  `stream` may be NULL = the calling thread's private stream.  Batched calls are
+ * asynchronous with respect to the host; use acgpu_stream_sync() or events.
+ */
+#ifndef ACGPU_H
+#define ACGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ac.h"
+#include "imgconvert.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct acgpu_stream_s *acgpu_stream_t;   /* a CUDA stream */
+typedef struct acgpu_event_s  *acgpu_event_t;    /* a CUDA event  */
+
+/* ---- library / device ------------------------------------------------------------------- */
+const char *acgpu_version(void);
+const char *acgpu_last_error(void);
+int  acgpu_device_count(void);
+int  acgpu_set_device(int ordinal);
+int  acgpu_get_device(void);
+int  acgpu_device_sm_count(void);
+/* Which kernel tier served the calling thread's last conversion: 0 none, 1 generic (any size or
+ * alignment), 2 vectorised (16-byte aligned planes), 3 TMA-staged.  For tests and profiling. */
+int  acgpu_last_kernel_tier(void);
+/* Number of kernel launches issued by the calling thread since the last reset (bench.py's
+ * `gpu_launches`). */
+uint64_t acgpu_launch_count(int reset);
+/* Force a tier for ac_imgconvert / acgpu_imgconvert_batch on this thread: 0 = automatic. */
+void acgpu_force_tier(int tier);
+
+/* ---- memory, streams, events ------------------------------------------------------------ */
+void *acgpu_malloc(size_t bytes);                 /* device memory, 256-byte aligned */
+void  acgpu_free(void *dptr);
+void *acgpu_host_alloc(size_t bytes);             /* page-locked host memory */
+void  acgpu_host_free(void *hptr);
+int   acgpu_memcpy_h2d(void *dptr, const void *hptr, size_t bytes, acgpu_stream_t stream);
+int   acgpu_memcpy_d2h(void *hptr, const void *dptr, size_t bytes, acgpu_stream_t stream);
+int   acgpu_memcpy_d2d(void *dptr, const void *sptr, size_t bytes, acgpu_stream_t stream);
+int   acgpu_memset(void *dptr, int value, size_t bytes, acgpu_stream_t stream);
+
+acgpu_stream_t acgpu_stream_create(void);
+void  acgpu_stream_destroy(acgpu_stream_t s);
+int   acgpu_stream_sync(acgpu_stream_t s);
+acgpu_event_t acgpu_event_create(void);
+void  acgpu_event_destroy(acgpu_event_t e);
+int   acgpu_event_record(acgpu_event_t e, acgpu_stream_t s);
+int   acgpu_event_sync(acgpu_event_t e);
+float acgpu_event_elapsed_ms(acgpu_event_t start, acgpu_event_t stop);
+
+/* ---- batched ac_imgconvert --------------------------------------------------------------- */
+/*
+ * Converts `nframes` frames in one go.  src[p] / dest[p] are DEVICE pointers to plane p of frame 0
+ * (planes[0] only for packed formats, exactly as ac_imgconvert); plane p of frame k lives
+ * src_frame_pitch / dest_frame_pitch bytes further per frame.  Arithmetic, untouched bytes and the
+ * YV12 alias are those of ac_imgconvert (aclib/imgconvert.c:34-64).  Unlike the reference's
+ * UYVY/YVYU -> planar wrapper (aclib/img_yuv_mixed.c:24-36) the source is never modified.
+ */
+int acgpu_imgconvert_batch(uint8_t *const *src, ImageFormat srcfmt, size_t src_frame_pitch,
+                           uint8_t *const *dest, ImageFormat destfmt, size_t dest_frame_pitch,
+                           int width, int height, int nframes, acgpu_stream_t stream);
+
+/*
+ * Host-buffer form of the same: frames are tightly packed (YUV_INIT_PLANES layout) one after the
+ * other in `src_frames` / `dest_frames` (best: acgpu_host_alloc memory).  Copies and kernels of
+ * successive chunks are overlapped on internal streams; returns after everything has landed in
+ * dest_frames.  This is the call bench.py's end-to-end number goes through.
+ */
+int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt,
+                                 uint8_t *dest_frames, ImageFormat destfmt,
+                                 int width, int height, int nframes);
+
+/* ---- batched ac_average / ac_rescale ------------------------------------------------------ */
+/*
+ * One row operation: dest_row = blend(src1_row, src2_row) with ac_rescale's exact rules
+ * (aclib/rescale.c:23-46: weight1 >= 65536 copies src1 and never reads src2; else weight2 >= 65536
+ * copies src2; else (a*w1 + b*w2 + 32768) >> 16 in uint32, low byte kept), or ac_average's
+ * (aclib/average.c:33-39) when `op` is ACGPU_ROW_AVERAGE.  Offsets are byte offsets from the frame
+ * base pointers given to acgpu_rowops_run().
+ */
+enum { ACGPU_ROW_RESCALE = 0, ACGPU_ROW_AVERAGE = 1, ACGPU_ROW_COPY = 2, ACGPU_ROW_AVERAGE3 = 3 };
+typedef struct {
+    int64_t  src1_off, src2_off, src3_off, dest_off;
+    uint32_t weight1, weight2;
+    uint32_t op;       /* ACGPU_ROW_*; AVERAGE3 = average(src3, average(src1, src2)), the fused form of
+                          tcv_deinterlace's linear blend (libtcvideo/tcvideo.c:368-389) */
+    uint32_t reserved;
+} acgpu_rowop;
+
+/* Runs `nops` row operations of `row_bytes` bytes on each of `nframes` frames with one launch.
+ * `ops` is a HOST array (copied to the device, cached by content).  Rows must not depend on rows
+ * written by the same call. */
+int acgpu_rowops_run(const uint8_t *src, size_t src_frame_pitch, uint8_t *dest, size_t dest_frame_pitch,
+                     const acgpu_rowop *ops, int nops, int row_bytes, int nframes, acgpu_stream_t stream);
+
+/* Device-pointer, single-call forms (the kernels behind the legacy ac_average / ac_rescale). */
+int acgpu_average(const uint8_t *src1, const uint8_t *src2, uint8_t *dest, size_t bytes, acgpu_stream_t stream);
+int acgpu_rescale(const uint8_t *src1, const uint8_t *src2, uint8_t *dest, size_t bytes,
+                  uint32_t weight1, uint32_t weight2, acgpu_stream_t stream);
+
+/* ---- frame-granular libtcvideo shapes (device-resident) ----------------------------------- */
+enum { ACGPU_DEINT_INTERPOLATE = 0, ACGPU_DEINT_LINEAR_BLEND = 1 };
+/* tcv_deinterlace INTERPOLATE / LINEAR_BLEND (libtcvideo/tcvideo.c:340-389) on nframes frames of
+ * width x height x Bpp bytes.  Unlike the reference's linear blend, src is left intact. */
+int acgpu_deinterlace_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, int mode,
+                            size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+/* tcv_resize (libtcvideo/tcvideo.c:427-531): exactly one of resize_w / resize_h may be non-zero. */
+int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp,
+                       int resize_w, int resize_h, int scale_w, int scale_h,
+                       size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACGPU_H */

@@ -10,7 +10,6 @@ Nothing under transcode-tcforge_b200/ imports this module.
 from __future__ import annotations
 
 import ctypes as C
-import importlib.util
 import os
 import subprocess
 import sys
@@ -20,11 +19,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 
-_spec = importlib.util.spec_from_file_location(
-    "acgpu_formats", os.path.join(ROOT, "transcode-tcforge_b200", "formats.py"))
-F = importlib.util.module_from_spec(_spec)
-sys.modules["acgpu_formats"] = F
-_spec.loader.exec_module(F)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import __graft_entry__ as _entry  # noqa: E402
+
+F = _entry.load_package().F     # format ids / plane sizes only; no pixel code comes from the product
 
 _u8p = C.POINTER(C.c_uint8)
 

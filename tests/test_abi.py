@@ -1,0 +1,100 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports exactly what include/*.h
+declares, keeps aclib's flag vocabulary (aclib/accore.c:76-167) and fails loudly without a device."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import __graft_entry__ as entry
+
+pkg = entry.load_package()
+ROOT = entry.ROOT
+
+
+@pytest.fixture(scope="module")
+def ac():
+    if not os.path.exists(pkg.LIB_PATH):
+        entry.build()
+    return pkg.AcGpu()
+
+
+def declared_symbols():
+    names = set()
+    for hdr in ("ac.h", "imgconvert.h", "acgpu.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(ac_[a-z_0-9]+|acgpu_[a-z_0-9]+)\s*\(", text))
+    return {n for n in names if not n.endswith("_t")}
+
+
+def test_library_exports_every_declared_symbol(ac):
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    decl = declared_symbols()
+    assert decl == set(pkg.ABI_SYMBOLS), decl ^ set(pkg.ABI_SYMBOLS)
+    assert decl <= exported, decl - exported
+    # nothing but the C ABI leaks out
+    assert all(s.startswith(("ac_", "acgpu_")) for s in exported), exported
+
+
+def test_reference_symbols_are_all_present(ac):
+    """The ten functions of aclib/ac.h:59-91 + aclib/imgconvert.h:81-90."""
+    for name in ["ac_init", "ac_cpuinfo", "ac_endian", "ac_flagstotext", "ac_parseflags", "ac_memcpy",
+                 "ac_average", "ac_rescale", "ac_imgconvert_init", "ac_imgconvert"]:
+        assert hasattr(ac.lib, name)
+
+
+def test_flag_vocabulary(ac):
+    assert ac.ac_flagstotext(0) == "none"
+    assert ac.ac_flagstotext(pkg.AC_CUDA) == "cuda"
+    assert ac.ac_flagstotext(0x8000 | 0x0100 | 0x0080 | 0x0008 | 0x0002) == "cuda sse2 sse mmx asm"
+    assert ac.ac_parseflags("cuda") == (1, 0x8000)
+    assert ac.ac_parseflags("CUDA,sse2,mmx") == (1, 0x8108)
+    assert ac.ac_parseflags("C") == (1, 0)
+    assert ac.ac_parseflags("asm") == (1, 0x0002)
+    assert ac.ac_parseflags("sse6")[0] == 0
+    assert ac.ac_parseflags("")[0] == 0
+    for text in ["sse5", "sse4a", "sse42", "sse41", "ssse3", "sse3", "sse2", "sse", "3dnowext", "3dnow", "mmxext", "mmx", "cmove"]:
+        ok, v = ac.ac_parseflags(text)
+        assert ok == 1 and ac.ac_flagstotext(v) == text
+
+
+def test_endianness(ac):
+    import sys
+    assert ac.lib.ac_endian() == (1 if sys.byteorder == "little" else 2)
+
+
+def test_host_memcpy_is_memmove(ac):
+    """ac.h:80-82: ascending copy, so overlapping dest<src works (decode_lavc.c:296-305 relies on it)."""
+    import numpy as np
+    a = np.arange(64, dtype=np.uint8)
+    ac.lib.ac_memcpy(a.ctypes.data, a.ctypes.data + 1, 63)
+    assert list(a[:63]) == list(range(1, 64))
+
+
+def test_fails_loudly_without_a_device(ac):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    assert ac.ac_cpuinfo() == 0
+    assert ac.ac_init(pkg.AC_ALL) == 0
+    assert "no CPU fallback" in ac.last_error()
+    import numpy as np
+    src = np.zeros(64 * 16 * 3 // 2, dtype=np.uint8)
+    ok, _ = ac.convert(src, pkg.F.IMG_YUV420P, pkg.F.IMG_RGB24, 64, 16)
+    assert ok == 0       # never silently computed on the CPU
+
+
+def test_product_never_touches_the_oracle():
+    """The product path must not import, link or load anything under oracle/."""
+    for dirpath, _, files in os.walk(entry.PKG_DIR):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile", ".map")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for needle in ("liboracle", "ac_oracle", "oracle_", "oracle/", "libac_ref", "checkers"):
+                    assert needle not in text, f"{f} references {needle}"
+    out = subprocess.run(["ldd", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libac_ref" not in out

@@ -1,0 +1,244 @@
+"""Parity tests proper (-m gpu): libacgpu's CUDA path, called through its C ABI, against the checker.
+
+The checker is the unmodified reference (oracle/_ref, ac_init(AC_NONE)) when its build travelled with
+the repo, else the restatement (oracle/liboracle.so); both are pinned to each other by test_oracle.py.
+Everything here is integer/byte work, so the bar is bit-exact, including bytes the C path leaves
+untouched (dest is pre-filled with 0x55) and 64-byte guard bands.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+import checkers as ck
+from checkers import F
+
+pkg = entry.load_package()
+pytestmark = pytest.mark.gpu
+
+ALL_PAIRS = [(s, d) for s in F.FORMATS_16 for d in F.FORMATS_16]
+CFG2_SRC = [F.IMG_YUV420P, F.IMG_YUV422P, F.IMG_YUV444P, F.IMG_YUY2, F.IMG_UYVY, F.IMG_Y8]
+CFG2_DST = [F.IMG_RGB24, F.IMG_BGR24, F.IMG_RGBA32]
+
+
+@pytest.fixture(scope="module")
+def ac():
+    a = pkg.AcGpu()
+    assert a.ac_cpuinfo() & pkg.AC_CUDA, "no usable B200"
+    assert a.ac_init(pkg.AC_ALL) == 1, a.last_error()
+    return a
+
+
+@pytest.fixture(scope="module")
+def chk():
+    return ck.best_checker()
+
+
+def size_variants(srcfmt, dstfmt, w, h):
+    uw, uh = F.size_unit(srcfmt, dstfmt)
+    return [(w, h), (w - uw, h), (w, h - uh), (w - uw, h - uh)]
+
+
+def assert_same(got, want, what):
+    if not np.array_equal(got, want):
+        bad = np.flatnonzero(got != want)
+        raise AssertionError(f"{what}: {bad.size} bytes differ, first at {bad[0]} (got {got[bad[0]]}, want {want[bad[0]]})")
+
+
+# ---- every pair, legacy host-pointer API, the reference test's four size variants -----------------
+@pytest.mark.parametrize("srcfmt,dstfmt", ALL_PAIRS, ids=lambda f: F.NAMES[f])
+def test_all_pairs_legacy_api_small(ac, chk, srcfmt, dstfmt):
+    for (w, h) in size_variants(srcfmt, dstfmt, 64, 16):
+        src = ck.random_frame(srcfmt, w, h, seed=1)
+        ok, got = ac.convert(src, srcfmt, dstfmt, w, h)
+        ok2, want = chk.convert(src, srcfmt, dstfmt, w, h)
+        assert ok == 1 and ok2 == 1, ac.last_error()
+        assert_same(got, want, f"{F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} @ {w}x{h}")
+
+
+# ---- every pair, batched device-resident API on an aligned size (vectorised tiers) + forced tier 1 --
+@pytest.mark.parametrize("srcfmt,dstfmt", ALL_PAIRS, ids=lambda f: F.NAMES[f])
+def test_all_pairs_batched_aligned(ac, chk, srcfmt, dstfmt):
+    w, h, nf = 128, 8, 3
+    frames = np.stack([ck.random_frame(srcfmt, w, h, seed=20 + i) for i in range(nf)])
+    dfb = F.frame_bytes(dstfmt, w, h)
+    want = np.stack([chk.convert(frames[i], srcfmt, dstfmt, w, h, pad=0)[1] for i in range(nf)])
+    for tier in (0, 1):
+        ac.lib.acgpu_force_tier(tier)
+        try:
+            got = ac.convert_batch(frames, srcfmt, dstfmt, w, h, dst_pitch=dfb + 256)
+        finally:
+            ac.lib.acgpu_force_tier(0)
+        assert_same(got[:, :dfb], want, f"batched {F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} tier {tier}")
+        assert (got[:, dfb:] == 0x55).all(), "wrote into the inter-frame gap"
+
+
+def test_unknown_pairs_and_degenerate_sizes(ac):
+    src = np.zeros(4096, np.uint8)
+    assert ac.convert(src, 0x1234, F.IMG_RGB24, 8, 8)[0] == 0          # imgconvert.c:63
+    assert ac.convert(src, F.IMG_RGB24, 0, 8, 8)[0] == 0
+    ok, d = ac.convert(src, F.IMG_YUV420P, F.IMG_RGB24, 0, 8)            # loops do not iterate
+    assert ok == 1 and (d == 0x55).all()
+    ok, d = ac.convert(src, F.IMG_YUV420P, F.IMG_RGB24, 8, 0)
+    assert ok == 1 and (d == 0x55).all()
+
+
+def test_golden_digests_through_libacgpu(ac):
+    with open(os.path.join(os.path.dirname(__file__), "golden", "imgconvert_digests.json")) as f:
+        gold = json.load(f)
+    for key, want in gold["digests"].items():
+        sname, dname, size = key.split(":")
+        w, h = map(int, size.split("x"))
+        sf, df = F.BY_NAME[sname], F.BY_NAME[dname]
+        src = ck.random_frame(sf, w, h, seed=gold["seed"])
+        ok, got = ac.convert(src, sf, df, w, h, prefill=0x55)
+        assert ok == 1 and hashlib.sha256(got.tobytes()).hexdigest()[:16] == want, key
+
+
+# ---- the reference test's own image and sizes (testsuite/test-imgconvert.c:180-224,361-363) ------------
+@pytest.mark.parametrize("srcfmt,dstfmt", [
+    (F.IMG_YUV420P, F.IMG_RGB24), (F.IMG_RGB24, F.IMG_YUV422P), (F.IMG_YUY2, F.IMG_YUV420P),
+    (F.IMG_YUV444P, F.IMG_BGRA32), (F.IMG_UYVY, F.IMG_YUV411P), (F.IMG_YUV411P, F.IMG_YVYU),
+    (F.IMG_ARGB32, F.IMG_YV12), (F.IMG_GRAY8, F.IMG_YUV420P), (F.IMG_Y8, F.IMG_ABGR32),
+    (F.IMG_YUV444P, F.IMG_YUV420P), (F.IMG_RGBA32, F.IMG_BGR24), (F.IMG_BGR24, F.IMG_GRAY8),
+], ids=lambda f: F.NAMES[f])
+def test_reference_test_image_768x512(ac, chk, srcfmt, dstfmt):
+    img = ck.glibc_random_bytes(768 * 512 * 4, 0)
+    for (w, h) in size_variants(srcfmt, dstfmt, 768, 512):
+        src = img[: F.frame_bytes(srcfmt, w, h)]
+        ok, got = ac.convert(src, srcfmt, dstfmt, w, h, prefill=0)
+        _, want = chk.convert(src, srcfmt, dstfmt, w, h, prefill=0)
+        assert ok == 1
+        assert_same(got, want, f"{F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} @ {w}x{h}")
+
+
+# ---- BASELINE config 2: the 36-pair matrix at 1920x1080, both directions ---------------------------------
+@pytest.mark.parametrize("a,b", [(s, d) for s in CFG2_SRC for d in CFG2_DST], ids=lambda f: F.NAMES[f])
+def test_config2_matrix_1080p(ac, chk, a, b):
+    w, h = 1920, 1080
+    for sf, df in ((a, b), (b, a)):
+        src = ck.random_frame(sf, w, h, seed=5)
+        got = ac.convert_batch(src[None, :], sf, df, w, h)[0]
+        _, want = chk.convert(src, sf, df, w, h, pad=0)
+        assert_same(got, want, f"1080p {F.NAMES[sf]}->{F.NAMES[df]}")
+
+
+def test_config1_pal_and_config4_uhd_round_trip(ac, chk):
+    # config 1 size (PAL; chroma pitch 360 is not 16-byte aligned) and config 4 (UHD 420P->RGB24->422P)
+    w, h = 720, 576
+    src = ck.random_frame(F.IMG_YUV420P, w, h, seed=9)
+    got = ac.convert_batch(src[None, :], F.IMG_YUV420P, F.IMG_RGB24, w, h)[0]
+    assert_same(got, chk.convert(src, F.IMG_YUV420P, F.IMG_RGB24, w, h, pad=0)[1], "PAL 420P->RGB24")
+    w, h = 3840, 2160
+    src = ck.random_frame(F.IMG_YUV420P, w, h, seed=9)
+    rgb = ac.convert_batch(src[None, :], F.IMG_YUV420P, F.IMG_RGB24, w, h)[0]
+    assert_same(rgb, chk.convert(src, F.IMG_YUV420P, F.IMG_RGB24, w, h, pad=0)[1], "UHD 420P->RGB24")
+    yuv = ac.convert_batch(rgb[None, :], F.IMG_RGB24, F.IMG_YUV422P, w, h)[0]
+    assert_same(yuv, chk.convert(rgb, F.IMG_RGB24, F.IMG_YUV422P, w, h, pad=0)[1], "UHD RGB24->422P")
+
+
+def test_config5_batch_64x720p_yuy2_to_420p(ac, chk):
+    w, h, nf = 1280, 720, 64
+    base = ck.random_frame(F.IMG_YUY2, w, h, seed=11)
+    frames = np.stack([np.roll(base, 977 * i) for i in range(nf)])
+    got = ac.convert_batch(frames, F.IMG_YUY2, F.IMG_YUV420P, w, h)
+    for i in (0, 1, 31, 63):
+        assert_same(got[i], chk.convert(frames[i], F.IMG_YUY2, F.IMG_YUV420P, w, h, pad=0)[1], f"720p frame {i}")
+    # every frame is a rolled copy of frame 0's bytes, so checksums of all outputs must be distinct and stable
+    sums = {hashlib.sha256(got[i].tobytes()).hexdigest() for i in range(nf)}
+    assert len(sums) == nf
+
+
+# ---- exhaustive cubes (SURVEY.md 8d iii) -------------------------------------------------------------------
+def test_exhaustive_yuv_cube_to_rgb(ac, chk):
+    """All 2^24 (Y,U,V) triples as a 4096x4096 YUV444P image -> RGB24 and -> BGRA32."""
+    n = 1 << 24
+    idx = np.arange(n, dtype=np.uint32)
+    src = np.concatenate([(idx & 0xFF).astype(np.uint8), ((idx >> 8) & 0xFF).astype(np.uint8), (idx >> 16).astype(np.uint8)])
+    w = h = 4096
+    got = ac.convert_batch(src[None, :], F.IMG_YUV444P, F.IMG_RGB24, w, h)[0]
+    assert_same(got, chk.convert(src, F.IMG_YUV444P, F.IMG_RGB24, w, h, pad=0)[1], "YUV cube -> RGB24")
+    got = ac.convert_batch(src[None, :], F.IMG_YUV444P, F.IMG_BGRA32, w, h)[0]
+    assert_same(got, chk.convert(src, F.IMG_YUV444P, F.IMG_BGRA32, w, h, pad=0)[1], "YUV cube -> BGRA32")
+
+
+def test_exhaustive_rgb_cube_to_yuv(ac, chk):
+    n = 1 << 24
+    idx = np.arange(n, dtype=np.uint32)
+    src = np.stack([(idx & 0xFF).astype(np.uint8), ((idx >> 8) & 0xFF).astype(np.uint8), (idx >> 16).astype(np.uint8)], axis=1).reshape(-1)
+    w = h = 4096
+    for df in (F.IMG_YUV444P, F.IMG_YUV420P, F.IMG_YUY2, F.IMG_GRAY8):
+        got = ac.convert_batch(src[None, :], F.IMG_RGB24, df, w, h)[0]
+        assert_same(got, chk.convert(src, F.IMG_RGB24, df, w, h, pad=0)[1], f"RGB cube -> {F.NAMES[df]}")
+
+
+# ---- size-independent properties at full size ----------------------------------------------------------------
+def test_properties_full_size(ac):
+    w, h = 1920, 1080
+    src = ck.random_frame(F.IMG_RGBA32, w, h, seed=2)
+    # pure permutes are involutions / invertible: RGBA -> ABGR -> RGBA, RGBA -> BGRA -> RGBA
+    for mid in (F.IMG_ABGR32, F.IMG_BGRA32, F.IMG_ARGB32):
+        a = ac.convert_batch(src[None, :], F.IMG_RGBA32, mid, w, h)[0]
+        b = ac.convert_batch(a[None, :], mid, F.IMG_RGBA32, w, h)[0]
+        assert np.array_equal(b, src)
+    # packed YUV byte orders round-trip, planar up-sampling then box down-sampling is the identity
+    p = ck.random_frame(F.IMG_YUY2, w, h, seed=3)
+    for mid in (F.IMG_UYVY, F.IMG_YVYU):
+        a = ac.convert_batch(p[None, :], F.IMG_YUY2, mid, w, h)[0]
+        assert np.array_equal(ac.convert_batch(a[None, :], mid, F.IMG_YUY2, w, h)[0], p)
+    y = ck.random_frame(F.IMG_YUV420P, w, h, seed=4)
+    up = ac.convert_batch(y[None, :], F.IMG_YUV420P, F.IMG_YUV444P, w, h)[0]
+    assert np.array_equal(ac.convert_batch(up[None, :], F.IMG_YUV444P, F.IMG_YUV420P, w, h)[0], y)
+    # YV12 is YUV420P with the chroma planes exchanged
+    a = ac.convert_batch(y[None, :], F.IMG_YUV420P, F.IMG_RGB24, w, h)[0]
+    p0, c = w * h, (w // 2) * (h // 2)
+    yv = np.concatenate([y[:p0], y[p0 + c:], y[p0:p0 + c]])
+    assert np.array_equal(ac.convert_batch(yv[None, :], F.IMG_YV12, F.IMG_RGB24, w, h)[0], a)
+    # alpha stays whatever the destination held (img_yuv_rgb.c:62-64)
+    out = ac.convert_batch(y[None, :], F.IMG_YUV420P, F.IMG_RGBA32, w, h, prefill=0xA7)[0]
+    assert (out[3::4] == 0xA7).all() and np.array_equal(out.reshape(-1, 4)[:, :3].reshape(-1), a)
+
+
+def test_in_place_packed_and_rgba_permutes(ac, chk):
+    """img_yuv_packed.c:22,29,40 and img_rgb_packed.c:22,44: these work with src == dest."""
+    w, h = 128, 16
+    for sf, df in [(F.IMG_YUY2, F.IMG_UYVY), (F.IMG_YUY2, F.IMG_YVYU), (F.IMG_UYVY, F.IMG_YVYU), (F.IMG_YVYU, F.IMG_UYVY),
+                   (F.IMG_RGBA32, F.IMG_ABGR32), (F.IMG_RGBA32, F.IMG_BGRA32), (F.IMG_ARGB32, F.IMG_RGBA32), (F.IMG_RGBA32, F.IMG_ARGB32)]:
+        src = ck.random_frame(sf, w, h, seed=6)
+        buf = ac.malloc(src.size).upload(src)
+        for tier in (0, 1):
+            buf.upload(src)
+            ac.lib.acgpu_force_tier(tier)
+            try:
+                ac._ok(ac.imgconvert_batch(buf.ptr, sf, src.size, buf.ptr, df, src.size, w, h, 1))
+            finally:
+                ac.lib.acgpu_force_tier(0)
+            ac.sync()
+            assert_same(buf.download(), chk.convert(src, sf, df, w, h, pad=0)[1], f"in-place {F.NAMES[sf]}->{F.NAMES[df]} tier {tier}")
+        buf.free()
+
+
+def test_uyvy_source_is_not_modified(ac):
+    """Documented difference: the reference rewrites UYVY/YVYU sources (img_yuv_mixed.c:24,30-32); libacgpu does not."""
+    w, h = 64, 16
+    src = ck.random_frame(F.IMG_UYVY, w, h, seed=8)
+    s = src.copy()
+    d = np.zeros(F.frame_bytes(F.IMG_YUV420P, w, h), np.uint8)
+    assert ac.ac_imgconvert(s, F.IMG_UYVY, d, F.IMG_YUV420P, w, h) == 1
+    assert np.array_equal(s, src)
+
+
+def test_odd_heights_and_widths_where_the_c_path_is_well_defined(ac, chk):
+    cases = [(F.IMG_YUV422P, F.IMG_RGB24, 64, 15), (F.IMG_YUY2, F.IMG_YUV422P, 62, 7), (F.IMG_YUV444P, F.IMG_RGB24, 37, 11),
+             (F.IMG_RGB24, F.IMG_YUV444P, 33, 9), (F.IMG_RGB24, F.IMG_GRAY8, 31, 5), (F.IMG_RGBA32, F.IMG_RGB24, 17, 3),
+             (F.IMG_YUV444P, F.IMG_YUV422P, 64, 5), (F.IMG_YUV422P, F.IMG_YUV444P, 66, 3), (F.IMG_Y8, F.IMG_RGBA32, 13, 13),
+             (F.IMG_YUV411P, F.IMG_YUV444P, 68, 5), (F.IMG_YUV422P, F.IMG_YUY2, 66, 5), (F.IMG_GRAY8, F.IMG_UYVY, 10, 3)]
+    for sf, df, w, h in cases:
+        src = ck.random_frame(sf, w, h, seed=12)
+        ok, got = ac.convert(src, sf, df, w, h)
+        _, want = chk.convert(src, sf, df, w, h)
+        assert ok == 1
+        assert_same(got, want, f"{F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h}")

@@ -1,0 +1,74 @@
+// acgpu_internal.h -- declarations shared by libacgpu's translation units (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "acgpu.h"
+
+namespace acgpu {
+
+// ---------------------------------------------------------------------------------------------
+// Format descriptors.  One struct describes any of the 15 layouts; kernels take it by value.
+// Offsets follow the reference tables: packed YUV (aclib/img_yuv_rgb.c:104-106), RGB byte orders
+// (aclib/img_yuv_rgb.c:129-134), planar subsampling (aclib/imgconvert.h:54-59).
+
+enum Kind : int { K_NONE = 0, K_PLANAR, K_Y8, K_PACKED, K_RGB, K_GRAY };
+
+struct FmtDesc {
+    int kind;
+    int sx, sy;              // K_PLANAR: log2 chroma subsampling (x, y)
+    int yo, uo, vo;          // K_PACKED: byte offsets inside the 4-byte (2-pixel) group
+    int bpp, ro, go, bo, ao; // K_RGB: bytes per pixel and channel offsets, ao < 0 when no alpha
+};
+
+FmtDesc describe(int fmt);
+size_t  frame_bytes(int fmt, int w, int h);
+size_t  chroma_plane_bytes(int fmt, int w, int h);
+int     nplanes(int fmt);
+
+// Batch geometry handed to every conversion launcher: plane pointers of frame 0 and the byte
+// distance between consecutive frames (one pitch for all planes of an image).
+struct Image {
+    uint8_t *p[3];
+    size_t   pitch;
+};
+
+struct ConvertArgs {
+    Image src, dst;
+    int   srcfmt, dstfmt;    // YV12 already folded into YUV420P with swapped planes
+    int   w, h, nframes;
+    cudaStream_t stream;
+};
+
+// Tier 1: any size, any alignment, literal loop bounds (kernels_generic.cu).
+bool convert_generic(const ConvertArgs &a);
+// Tier 2: 16-byte vectorised kernels; returns false (without launching) when the pair/size/alignment
+// is outside its domain so the caller can fall back to tier 1 (kernels_fast.cu).
+bool convert_fast(const ConvertArgs &a);
+// Tier 3: TMA/bulk-copy staged persistent kernels for the headline pairs (kernels_tma.cu).
+bool convert_tma(const ConvertArgs &a);
+
+// Row blends (rowops.cu).
+bool rowops_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
+                   const acgpu_rowop *d_ops, int nops, int row_bytes, int nframes, cudaStream_t st,
+                   bool offsets_aligned16);
+bool blend_launch(const uint8_t *s1, const uint8_t *s2, uint8_t *d, size_t bytes,
+                  uint32_t w1, uint32_t w2, int op, cudaStream_t st);
+bool resize_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
+                     const int32_t *d_source, const uint32_t *d_w1, const uint32_t *d_w2,
+                     int width, int new_w, int new_h, int Bpp, int scale_w, int nframes, cudaStream_t st);
+
+// Per-thread bookkeeping (host_api.cu).
+void     note_launch(int n = 1);
+void     set_error(const char *fmt, ...);
+bool     check(cudaError_t e, const char *what);
+int      sm_count();
+
+}  // namespace acgpu
+
+#define ACGPU_CHECK_LAUNCH(what)                                   \
+    do {                                                           \
+        if (!::acgpu::check(cudaGetLastError(), what)) return false; \
+    } while (0)
