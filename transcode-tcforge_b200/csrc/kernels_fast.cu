@@ -1,5 +1,398 @@
-// kernels_fast.cu -- tier 2 (vectorised) conversions.  Filled in below the generic tier.
+// kernels_fast.cu -- tier 2: bandwidth-oriented conversions (16-byte vector accesses, one launch per batch).
+//
+// Shape shared by every kernel here: a thread owns a *unit* of 16 horizontally adjacent pixels (two rows
+// of them when a 4:2:0 plane is involved, so each chroma sample is loaded and decoded once), the 32 units
+// of a warp are contiguous in memory, planar operands are read/written as one 128-bit (luma) or 64-bit
+// (chroma) access per lane, and byte-interleaved operands (24/32-bit RGB, packed YUV) go through a per-warp
+// shared-memory transpose so that every global store instruction writes 512 contiguous bytes.
+// Grids are persistent-ish: (blocks_x, frames) with blocks striding over rows / units of their frame.
+//
+// Arithmetic is the reduced integer form of pixmath.cuh (proved equal to the C path exhaustively).
+// Tensor cores are not used: a per-pixel 3x3 integer map with truncation rules is not a dense contraction,
+// and the path is HBM-bound (DESIGN.md section 4 has the instruction budget that makes it so).
+//
+// Domain: every plane pointer and frame pitch 16-byte aligned, sizes on the formats' unit grid, and
+// width % 16 == 0 when a 4:2:0 plane is involved (otherwise (width*height) % 16 == 0).  Outside it
+// convert_fast() returns false and the generic tier runs.
 #include "acgpu_internal.h"
+#include "pixmath.cuh"
+
 namespace acgpu {
-bool convert_fast(const ConvertArgs &) { return false; }
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// Chroma offset tables (aclib/img_yuv_rgb.c:50-55), built at compile time.  Entry layout is chosen so one
+// 64-bit shared load yields two ready-to-use terms:  v[i] = {rV[i] - 256, gV[i] - 256},  u[i] = {bU[i] - 256, gU[i]}
+// (the -256 is the Ylut origin shift, see pixmath::ylut_word_fast).
+struct ChromaTabs {
+    int v[512];
+    int u[512];
+};
+constexpr int chroma_term(int coef, int c) { return (coef * (c - 128) * 16 + 76309 / 2) / 76309; }
+constexpr ChromaTabs make_tabs()
+{
+    ChromaTabs t{};
+    for (int i = 0; i < 256; i++) {
+        t.v[2 * i] = chroma_term(pixmath::kCRV, i) - 256;
+        t.v[2 * i + 1] = chroma_term(pixmath::kCGV, i) - 256;
+        t.u[2 * i] = chroma_term(pixmath::kCBU, i) - 256;
+        t.u[2 * i + 1] = chroma_term(pixmath::kCGU, i);
+    }
+    return t;
+}
+__device__ const ChromaTabs g_tabs = make_tabs();
+
+// ---------------------------------------------------------------------------------------------------
+// Small device helpers
+
+__device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint2 ldg64(const uint8_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
+// streaming stores: the output is never re-read by this kernel
+__device__ __forceinline__ void stg128(uint8_t *p, uint4 v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
+__device__ __forceinline__ void stg64(uint8_t *p, uint2 v) { __stcs(reinterpret_cast<uint2 *>(p), v); }
+__device__ __forceinline__ void stg32(uint8_t *p, uint32_t v) { __stcs(reinterpret_cast<uint32_t *>(p), v); }
+
+__device__ __forceinline__ uint32_t word_of(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int b) { return (w >> (8 * b)) & 0xFFu; }
+
+// One colour channel: j = 16*Y + c (dp4a picks the Y byte and scales it), clamp j to [0, 3498], and the
+// answer is the TOP byte of j*1220944 + 2^23 (pixmath::ylut_word_fast).  3 instructions.
+__device__ __forceinline__ uint32_t channel_word(uint32_t yword, uint32_t ysel, int c)
+{
+    const int j = (int)__dp4a(yword, ysel, (uint32_t)c);
+    const int jc = __vimin_s32_relu(j, pixmath::kJMax);
+    return (uint32_t)jc * pixmath::kJMul + pixmath::kJAdd;
+}
+// (a.b3, b.b3, c.b3, d.b3) -> one word
+__device__ __forceinline__ uint32_t pack_top4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
+}
+
+// Per-warp staging: lane-owned chunks (each lane owns K consecutive 16-byte chunks of the warp's contiguous
+// output) are written to shared memory and read back in global order so every STG covers 512 contiguous bytes.
+// K = 3 needs no swizzle (48-byte lane stride is conflict-free); K = 4 / K = 2 XOR-swizzle the chunk slot.
+template <int K>
+__device__ __forceinline__ int stage_slot(int lane, int k)
+{
+    if (K == 4) return lane * 4 + (k ^ ((lane >> 1) & 3));
+    if (K == 2) return lane * 2 + (k ^ ((lane >> 2) & 1));
+    return lane * K + k;
+}
+template <int K>
+__device__ __forceinline__ int stage_slot_linear(int c)   // c = global chunk index inside the warp tile
+{
+    return stage_slot<K>(c / K, c % K);
+}
+
+enum SrcKind { S420 = 0, S422 = 1, S411 = 2, S444 = 3, SYUY2 = 4, SUYVY = 5, SYVYU = 6 };
+
+struct FastParams {
+    const uint8_t *s0, *s1, *s2;
+    uint8_t *d0, *d1, *d2;
+    size_t spitch, dpitch;
+    int w, h;
+    int upr;           // 4:2:0 mode: 16-pixel units per row
+    int nrp;           // 4:2:0 mode: row pairs
+    uint32_t nunits;   // linear mode: units per frame
+};
+
+// ---------------------------------------------------------------------------------------------------
+// K1: YUV (7 layouts) -> RGB (6 layouts).  aclib/img_yuv_rgb.c:58-136.
+//   SWAP   : first colour byte is B instead of R (BGR24, BGRA32, ABGR32)
+//   BPP    : 3 or 4;  AFIRST: alpha is byte 0 (ARGB32, ABGR32) -- alpha is never written: for BPP 4 the
+//            destination chunk is read, merged with a byte mask, and written back (read-modify-write).
+
+template <int SRC> struct SrcInfo {
+    static constexpr bool packed = SRC >= SYUY2;
+    static constexpr int nchroma = SRC == S444 ? 16 : SRC == S411 ? 4 : 8;   // chroma samples per 16 pixels
+    static constexpr int yo = SRC == SUYVY ? 1 : 0;
+    static constexpr int uo = SRC == SYUY2 ? 1 : SRC == SUYVY ? 0 : 3;
+    static constexpr int vo = SRC == SYUY2 ? 3 : SRC == SUYVY ? 2 : 1;
+};
+
+// Converts one row of 16 pixels.  yw: 4 words (planar luma) or 8 words (packed groups).
+// cr/cg/cb: per-chroma-sample offsets.  Emits BPP*4 words.
+template <int SRC, bool SWAP, int BPP, bool AFIRST>
+__device__ __forceinline__ void convert_row(const uint32_t *yw, const int *cr, const int *cg, const int *cb, uint32_t *out)
+{
+    using SI = SrcInfo<SRC>;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {          // 4 pixels per group
+        uint32_t xa[4], xg[4], xc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int px = g * 4 + k;
+            const int s = SI::nchroma == 16 ? px : SI::nchroma == 8 ? px / 2 : px / 4;
+            uint32_t word, sel;
+            if (SI::packed) {
+                word = yw[px / 2];
+                sel = 0x10u << (8 * ((px & 1) * 2 + SI::yo));
+            } else {
+                word = yw[g];
+                sel = 0x10u << (8 * k);
+            }
+            xa[k] = channel_word(word, sel, SWAP ? cb[s] : cr[s]);
+            xg[k] = channel_word(word, sel, cg[s]);
+            xc[k] = channel_word(word, sel, SWAP ? cr[s] : cb[s]);
+        }
+        if (BPP == 3) {
+            out[g * 3 + 0] = pack_top4(xa[0], xg[0], xc[0], xa[1]);
+            out[g * 3 + 1] = pack_top4(xg[1], xc[1], xa[2], xg[2]);
+            out[g * 3 + 2] = pack_top4(xc[2], xa[3], xg[3], xc[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t t = __byte_perm(xa[k], xg[k], 0x0073);
+                out[g * 4 + k] = AFIRST ? __byte_perm(t, xc[k], 0x7100) : __byte_perm(t, xc[k], 0x0710);
+            }
+        }
+    }
+}
+
+// Writes one row's 16 pixels per lane (BPP*4 words) through the warp staging buffer to `rowbase`
+// (the address of the warp's first unit).  nvalid = number of lanes holding real units (warp-uniform).
+template <int BPP, bool AFIRST>
+__device__ __forceinline__ void store_row_rgb(uint4 *stage, int lane, const uint32_t *ow, uint8_t *rowbase, int nvalid)
+{
+    constexpr int K = BPP;   // 16-byte chunks per lane
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        stage[stage_slot<K>(lane, k)] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+    __syncwarp();
+    const int nchunks = nvalid * K;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const int c = j * 32 + lane;
+        if (c < nchunks) {
+            uint4 v = stage[stage_slot_linear<K>(c)];
+            uint8_t *g = rowbase + (size_t)c * 16;
+            if (BPP == 4) {     // keep the destination's alpha bytes (img_yuv_rgb.c:62-64 never stores them)
+                const uint4 old = *reinterpret_cast<const uint4 *>(g);
+                const uint32_t m = AFIRST ? 0x000000FFu : 0xFF000000u;
+                v.x = (v.x & ~m) | (old.x & m);
+                v.y = (v.y & ~m) | (old.y & m);
+                v.z = (v.z & ~m) | (old.z & m);
+                v.w = (v.w & ~m) | (old.w & m);
+            }
+            stg128(g, v);
+        }
+    }
+    __syncwarp();
+}
+
+template <int SRC>
+__device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32_t V, int &cr, int &cg, int &cb)
+{
+    const int2 tv = tab[V], tu = tab[256 + U];
+    cr = tv.x;
+    cg = tv.y + tu.y;
+    cb = tu.x;
+}
+
+template <int SRC, bool SWAP, int BPP, bool AFIRST>
+__global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
+{
+    using SI = SrcInfo<SRC>;
+    __shared__ int2 s_tab[512];
+    extern __shared__ uint4 s_stage[];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *stage = s_stage + warp * (32 * BPP);
+    const size_t soff = (size_t)blockIdx.y * p.spitch, doff = (size_t)blockIdx.y * p.dpitch;
+    uint8_t *dst = p.d0 + doff;
+
+    if (SRC == S420) {
+        const uint8_t *Y = p.s0 + soff, *U = p.s1 + soff, *V = p.s2 + soff;
+        const int unit = threadIdx.x;
+        const bool valid = unit < p.upr;
+        const int nvalid = min(32, p.upr - warp * 32);
+        if (nvalid <= 0) return;
+        for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
+            uint32_t y0[4] = {0, 0, 0, 0}, y1[4] = {0, 0, 0, 0};
+            uint2 uu = make_uint2(0, 0), vv = make_uint2(0, 0);
+            if (valid) {
+                const uint8_t *yp = Y + (size_t)(2 * rp) * p.w + unit * 16;
+                const uint4 a = ldg128(yp), b = ldg128(yp + p.w);
+                y0[0] = a.x; y0[1] = a.y; y0[2] = a.z; y0[3] = a.w;
+                y1[0] = b.x; y1[1] = b.y; y1[2] = b.z; y1[3] = b.w;
+                const size_t co = (size_t)rp * (p.w >> 1) + unit * 8;
+                uu = ldg64(U + co);
+                vv = ldg64(V + co);
+            }
+            int cr[8], cg[8], cb[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                chroma_terms<SRC>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+            uint32_t ow[BPP * 4];
+            uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + warp * 512) * BPP;
+            convert_row<SRC, SWAP, BPP, AFIRST>(y0, cr, cg, cb, ow);
+            store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0, nvalid);
+            convert_row<SRC, SWAP, BPP, AFIRST>(y1, cr, cg, cb, ow);
+            store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+        }
+    } else {
+        const uint8_t *S0 = p.s0 + soff, *S1 = p.s1 + soff, *S2 = p.s2 + soff;
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t base = blockIdx.x * blockDim.x; base < p.nunits; base += stride) {
+            const uint32_t u = base + threadIdx.x;
+            const uint32_t warp_u0 = base + warp * 32;
+            if (warp_u0 >= p.nunits) break;                  // warp-uniform
+            const int nvalid = (int)min(32u, p.nunits - warp_u0);
+            const bool valid = u < p.nunits;
+            uint32_t yw[SI::packed ? 8 : 4];
+            int cr[SI::nchroma], cg[SI::nchroma], cb[SI::nchroma];
+            if (SI::packed) {
+                uint4 a = make_uint4(0, 0, 0, 0), b = a;
+                if (valid) { a = ldg128(S0 + (size_t)u * 32); b = ldg128(S0 + (size_t)u * 32 + 16); }
+                yw[0] = a.x; yw[1] = a.y; yw[2] = a.z; yw[3] = a.w;
+                yw[4] = b.x; yw[5] = b.y; yw[6] = b.z; yw[7] = b.w;
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    chroma_terms<SRC>(s_tab, byte_of(yw[s], SI::uo), byte_of(yw[s], SI::vo), cr[s], cg[s], cb[s]);
+            } else {
+                uint4 a = make_uint4(0, 0, 0, 0);
+                if (valid) a = ldg128(S0 + (size_t)u * 16);
+                yw[0] = a.x; yw[1] = a.y; yw[2] = a.z; yw[3] = a.w;
+                if (SRC == S444) {
+                    uint4 uu = make_uint4(0, 0, 0, 0), vv = uu;
+                    if (valid) { uu = ldg128(S1 + (size_t)u * 16); vv = ldg128(S2 + (size_t)u * 16); }
+#pragma unroll
+                    for (int s = 0; s < 16; s++)
+                        chroma_terms<SRC>(s_tab, byte_of(word_of(uu, s >> 2), s & 3), byte_of(word_of(vv, s >> 2), s & 3), cr[s], cg[s], cb[s]);
+                } else if (SRC == S422) {
+                    uint2 uu = make_uint2(0, 0), vv = uu;
+                    if (valid) { uu = ldg64(S1 + (size_t)u * 8); vv = ldg64(S2 + (size_t)u * 8); }
+#pragma unroll
+                    for (int s = 0; s < 8; s++)
+                        chroma_terms<SRC>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+                } else {   // S411
+                    uint32_t uu = 0, vv = 0;
+                    if (valid) { uu = ldg32(S1 + (size_t)u * 4); vv = ldg32(S2 + (size_t)u * 4); }
+#pragma unroll
+                    for (int s = 0; s < 4; s++) chroma_terms<SRC>(s_tab, byte_of(uu, s), byte_of(vv, s), cr[s], cg[s], cb[s]);
+                }
+            }
+            uint32_t ow[BPP * 4];
+            convert_row<SRC, SWAP, BPP, AFIRST>(yw, cr, cg, cb, ow);
+            store_row_rgb<BPP, AFIRST>(stage, lane, ow, dst + (size_t)warp_u0 * 16 * BPP, nvalid);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+
+inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+struct LaunchShape {
+    dim3 grid, block;
+};
+
+// 4:2:0 mode: one block spans a row pair (ceil(upr/32) warps), grid.x strides over row pairs.
+inline LaunchShape shape_420(int upr, int nrp, int nframes)
+{
+    LaunchShape s;
+    const int threads = ((upr + 31) / 32) * 32;
+    s.block = dim3(threads);
+    const int per_sm = 2048 / threads;
+    long want = (long)sm_count() * per_sm * 2;              // about two waves of resident blocks
+    long gx = (want + nframes - 1) / nframes;
+    if (gx < 1) gx = 1;
+    if (gx > nrp) gx = nrp;
+    s.grid = dim3((unsigned)gx, (unsigned)nframes);
+    return s;
+}
+
+inline LaunchShape shape_linear(uint32_t nunits, int nframes)
+{
+    LaunchShape s;
+    s.block = dim3(256);
+    long want = (long)sm_count() * 8 * 2;
+    long gx = (want + nframes - 1) / nframes;
+    const long maxgx = (nunits + 255) / 256;
+    if (gx < 1) gx = 1;
+    if (gx > maxgx) gx = maxgx;
+    s.grid = dim3((unsigned)gx, (unsigned)nframes);
+    return s;
+}
+
+template <int SRC, bool SWAP, int BPP, bool AFIRST>
+bool launch_yuv2rgb(const FastParams &p, int nframes, cudaStream_t st)
+{
+    LaunchShape s = SRC == S420 ? shape_420(p.upr, p.nrp, nframes) : shape_linear(p.nunits, nframes);
+    const size_t smem = (size_t)(s.block.x / 32) * 32 * BPP * sizeof(uint4);
+    k_yuv2rgb<SRC, SWAP, BPP, AFIRST><<<s.grid, s.block, smem, st>>>(p);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_yuv2rgb");
+    return true;
+}
+
+template <int SRC>
+bool dispatch_yuv2rgb_dst(int dstfmt, const FastParams &p, int nframes, cudaStream_t st)
+{
+    switch (dstfmt) {
+    case IMG_RGB24:  return launch_yuv2rgb<SRC, false, 3, false>(p, nframes, st);
+    case IMG_BGR24:  return launch_yuv2rgb<SRC, true, 3, false>(p, nframes, st);
+    case IMG_RGBA32: return launch_yuv2rgb<SRC, false, 4, false>(p, nframes, st);
+    case IMG_BGRA32: return launch_yuv2rgb<SRC, true, 4, false>(p, nframes, st);
+    case IMG_ARGB32: return launch_yuv2rgb<SRC, false, 4, true>(p, nframes, st);
+    case IMG_ABGR32: return launch_yuv2rgb<SRC, true, 4, true>(p, nframes, st);
+    default: return false;
+    }
+}
+
+bool fast_yuv2rgb(const ConvertArgs &a, const FastParams &p)
+{
+    switch (a.srcfmt) {
+    case IMG_YUV420P: return dispatch_yuv2rgb_dst<S420>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV422P: return dispatch_yuv2rgb_dst<S422>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV411P: return dispatch_yuv2rgb_dst<S411>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV444P: return dispatch_yuv2rgb_dst<S444>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUY2:    return dispatch_yuv2rgb_dst<SYUY2>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_UYVY:    return dispatch_yuv2rgb_dst<SUYVY>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YVYU:    return dispatch_yuv2rgb_dst<SYVYU>(a.dstfmt, p, a.nframes, a.stream);
+    default: return false;
+    }
+}
+
+}  // namespace
+
+bool convert_fast(const ConvertArgs &a)
+{
+    const FmtDesc sd = describe(a.srcfmt), dd = describe(a.dstfmt);
+    const int w = a.w, h = a.h;
+    if (w <= 0 || h <= 0 || a.nframes <= 0) return false;
+    // alignment domain
+    for (int i = 0; i < 3; i++)
+        if ((a.src.p[i] && !al16(a.src.p[i])) || (a.dst.p[i] && !al16(a.dst.p[i]))) return false;
+    if (a.nframes > 1 && (a.src.pitch % 16 || a.dst.pitch % 16)) return false;
+    const bool any420 = a.srcfmt == IMG_YUV420P || a.dstfmt == IMG_YUV420P;
+    const size_t P = (size_t)w * h;
+    if (any420) {
+        if (w % 16 || h % 2) return false;
+    } else {
+        if (P % 16) return false;
+        if ((a.srcfmt == IMG_YUV411P || a.dstfmt == IMG_YUV411P) && w % 4) return false;
+        if ((sd.kind == K_PACKED || dd.kind == K_PACKED || a.srcfmt == IMG_YUV422P || a.dstfmt == IMG_YUV422P) && w % 2) return false;
+    }
+    if (P / 16 > 0x7FFFFFFFu) return false;
+
+    FastParams p{};
+    p.s0 = a.src.p[0]; p.s1 = a.src.p[1]; p.s2 = a.src.p[2];
+    p.d0 = a.dst.p[0]; p.d1 = a.dst.p[1]; p.d2 = a.dst.p[2];
+    p.spitch = a.src.pitch; p.dpitch = a.dst.pitch;
+    p.w = w; p.h = h;
+    p.upr = w / 16; p.nrp = h / 2;
+    p.nunits = (uint32_t)(P / 16);
+
+    if ((sd.kind == K_PLANAR || sd.kind == K_PACKED) && dd.kind == K_RGB) {
+        if (any420 && p.upr > 1024) return false;
+        return fast_yuv2rgb(a, p);
+    }
+    return false;
+}
+
 }  // namespace acgpu
