@@ -283,6 +283,236 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2: RGB (6 layouts) -> YUV (7 layouts + Y8).  aclib/img_yuv_rgb.c:142-221.
+// Every pixel yields Y; chroma is POINT-sampled, never averaged: 4:2:0 takes U at (even x, even y) and V at
+// (odd x, odd y); 4:2:2 / packed take U at even x and V at odd x (YVYU: V at even x, U at odd x); 4:1:1 takes
+// U at x%4==0 and V at x%4==2.  Each component is two dp2a instructions on the pixel word (16-bit
+// coefficients x 8-bit samples) with the rounding constant and the +16/+128 offset folded into the
+// accumulator, so the answer is simply byte 2 of the accumulator.
+
+enum RgbLayout { L_RGB24 = 0, L_BGR24 = 1, L_RGBA = 2, L_BGRA = 3, L_ARGB = 4, L_ABGR = 5 };
+enum YuvDst { D420 = 0, D422 = 1, D411 = 2, D444 = 3, DYUY2 = 4, DUYVY = 5, DYVYU = 6, DY8 = 7 };
+
+template <int SL> struct RgbInfo {
+    static constexpr int bpp = SL <= L_BGR24 ? 3 : 4;
+    // byte position of each channel inside the (normalised) pixel word
+    static constexpr int rpos = (SL == L_RGB24 || SL == L_RGBA) ? 0 : (SL == L_BGR24 || SL == L_BGRA) ? 2 : SL == L_ARGB ? 1 : 3;
+    static constexpr int gpos = (SL == L_ARGB || SL == L_ABGR) ? 2 : 1;
+    static constexpr int bpos = (SL == L_RGB24 || SL == L_RGBA) ? 2 : (SL == L_BGR24 || SL == L_BGRA) ? 0 : SL == L_ARGB ? 3 : 1;
+    static constexpr uint32_t half(int kr, int kg, int kb, int p0)   // coefficients for byte positions p0, p0+1
+    {
+        const int c0 = rpos == p0 ? kr : gpos == p0 ? kg : bpos == p0 ? kb : 0;
+        const int c1 = rpos == p0 + 1 ? kr : gpos == p0 + 1 ? kg : bpos == p0 + 1 ? kb : 0;
+        return (uint32_t)(c0 & 0xFFFF) | ((uint32_t)(c1 & 0xFFFF) << 16);
+    }
+};
+
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_lo_su(uint32_t a, uint32_t b, uint32_t c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_su(uint32_t a, uint32_t b, uint32_t c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
+}
+
+// accumulators whose byte 2 is the component value
+template <int SL> __device__ __forceinline__ uint32_t acc_y(uint32_t px)
+{
+    using RI = RgbInfo<SL>;
+    constexpr uint32_t lo = RI::half(16829, 33039, 6416, 0), hi = RI::half(16829, 33039, 6416, 2);
+    return dp2a_hi_uu(hi, px, dp2a_lo_uu(lo, px, 32768u + (16u << 16)));
+}
+template <int SL> __device__ __forceinline__ uint32_t acc_u(uint32_t px)
+{
+    using RI = RgbInfo<SL>;
+    constexpr uint32_t lo = RI::half(-9714, -19070, 28784, 0), hi = RI::half(-9714, -19070, 28784, 2);
+    return dp2a_hi_su(hi, px, dp2a_lo_su(lo, px, 32768u + (128u << 16)));
+}
+template <int SL> __device__ __forceinline__ uint32_t acc_v(uint32_t px)
+{
+    using RI = RgbInfo<SL>;
+    constexpr uint32_t lo = RI::half(28784, -24103, -4681, 0), hi = RI::half(28784, -24103, -4681, 2);
+    return dp2a_hi_su(hi, px, dp2a_lo_su(lo, px, 32768u + (128u << 16)));
+}
+// (a.b2, b.b2, c.b2, d.b2) -> one word
+__device__ __forceinline__ uint32_t pack_b2x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0062), __byte_perm(c, d, 0x0062), 0x5410);
+}
+
+// Loads the 16 pixels of unit `u` of a row that starts at `row` into normalised pixel words.
+template <int SL>
+__device__ __forceinline__ void load_rgb16(const uint8_t *row, uint32_t u, bool valid, uint32_t *px)
+{
+    if (RgbInfo<SL>::bpp == 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) v = ldg128(row + (size_t)u * 64 + k * 16);
+            px[4 * k] = v.x; px[4 * k + 1] = v.y; px[4 * k + 2] = v.z; px[4 * k + 3] = v.w;
+        }
+    } else {
+        uint32_t w[12];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) v = ldg128(row + (size_t)u * 48 + k * 16);
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {   // 4 pixels = 3 words
+            px[4 * g + 0] = w[3 * g];
+            px[4 * g + 1] = __byte_perm(w[3 * g], w[3 * g + 1], 0x0543);
+            px[4 * g + 2] = __byte_perm(w[3 * g + 1], w[3 * g + 2], 0x0432);
+            px[4 * g + 3] = w[3 * g + 2] >> 8;
+        }
+    }
+}
+
+// Stores K lane-owned 16-byte chunks (words ow[0..4K)) through the staging buffer; plain coalesced write.
+template <int K>
+__device__ __forceinline__ void store_chunks(uint4 *stage, int lane, const uint32_t *ow, uint8_t *warpbase, int nvalid)
+{
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        stage[stage_slot<K>(lane, k)] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+    __syncwarp();
+    const int nchunks = nvalid * K;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const int c = j * 32 + lane;
+        if (c < nchunks) stg128(warpbase + (size_t)c * 16, stage[stage_slot_linear<K>(c)]);
+    }
+    __syncwarp();
+}
+
+template <int SL, int DST>
+__global__ void __launch_bounds__(256, 4) k_rgb2yuv(FastParams p)
+{
+    using RI = RgbInfo<SL>;
+    extern __shared__ uint4 s_stage[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *stage = s_stage + warp * 64;
+    const size_t soff = (size_t)blockIdx.y * p.spitch, doff = (size_t)blockIdx.y * p.dpitch;
+    const uint8_t *src = p.s0 + soff;
+    uint8_t *Y = p.d0 + doff, *U = p.d1 + doff, *V = p.d2 + doff;
+
+    if (DST == D420) {
+        const uint32_t unit = threadIdx.x;
+        const bool valid = (int)unit < p.upr;
+        if (min(32, p.upr - warp * 32) <= 0) return;
+        for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
+            uint32_t px[16], ay[16];
+            const uint8_t *row0 = src + (size_t)(2 * rp) * p.w * RI::bpp;
+            // row 0: Y everywhere, U from even pixels
+            load_rgb16<SL>(row0, unit, valid, px);
+#pragma unroll
+            for (int k = 0; k < 16; k++) ay[k] = acc_y<SL>(px[k]);
+            uint32_t uacc[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) uacc[k] = acc_u<SL>(px[2 * k]);
+            if (valid) {
+                stg128(Y + (size_t)(2 * rp) * p.w + unit * 16,
+                       make_uint4(pack_b2x4(ay[0], ay[1], ay[2], ay[3]), pack_b2x4(ay[4], ay[5], ay[6], ay[7]),
+                                  pack_b2x4(ay[8], ay[9], ay[10], ay[11]), pack_b2x4(ay[12], ay[13], ay[14], ay[15])));
+                stg64(U + (size_t)rp * (p.w >> 1) + unit * 8,
+                      make_uint2(pack_b2x4(uacc[0], uacc[1], uacc[2], uacc[3]), pack_b2x4(uacc[4], uacc[5], uacc[6], uacc[7])));
+            }
+            // row 1: Y everywhere, V from odd pixels
+            load_rgb16<SL>(row0 + (size_t)p.w * RI::bpp, unit, valid, px);
+#pragma unroll
+            for (int k = 0; k < 16; k++) ay[k] = acc_y<SL>(px[k]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) uacc[k] = acc_v<SL>(px[2 * k + 1]);
+            if (valid) {
+                stg128(Y + (size_t)(2 * rp + 1) * p.w + unit * 16,
+                       make_uint4(pack_b2x4(ay[0], ay[1], ay[2], ay[3]), pack_b2x4(ay[4], ay[5], ay[6], ay[7]),
+                                  pack_b2x4(ay[8], ay[9], ay[10], ay[11]), pack_b2x4(ay[12], ay[13], ay[14], ay[15])));
+                stg64(V + (size_t)rp * (p.w >> 1) + unit * 8,
+                      make_uint2(pack_b2x4(uacc[0], uacc[1], uacc[2], uacc[3]), pack_b2x4(uacc[4], uacc[5], uacc[6], uacc[7])));
+            }
+        }
+    } else {
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t base = blockIdx.x * blockDim.x; base < p.nunits; base += stride) {
+            const uint32_t u = base + threadIdx.x;
+            const uint32_t warp_u0 = base + warp * 32;
+            if (warp_u0 >= p.nunits) break;
+            const int nvalid = (int)min(32u, p.nunits - warp_u0);
+            const bool valid = u < p.nunits;
+            uint32_t px[16], ay[16];
+            load_rgb16<SL>(src, u, valid, px);
+#pragma unroll
+            for (int k = 0; k < 16; k++) ay[k] = acc_y<SL>(px[k]);
+            if (DST >= DYUY2 && DST <= DYVYU) {
+                // cells (Y, C): C = U of even pixels / V of odd pixels (YVYU: the other way round)
+                uint32_t ow[8];
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const uint32_t c0 = DST == DYVYU ? acc_v<SL>(px[2 * g]) : acc_u<SL>(px[2 * g]);
+                    const uint32_t c1 = DST == DYVYU ? acc_u<SL>(px[2 * g + 1]) : acc_v<SL>(px[2 * g + 1]);
+                    ow[g] = DST == DUYVY ? pack_b2x4(c0, ay[2 * g], c1, ay[2 * g + 1]) : pack_b2x4(ay[2 * g], c0, ay[2 * g + 1], c1);
+                }
+                store_chunks<2>(stage, lane, ow, Y + (size_t)warp_u0 * 32, nvalid);
+                continue;
+            }
+            if (valid)
+                stg128(Y + (size_t)u * 16,
+                       make_uint4(pack_b2x4(ay[0], ay[1], ay[2], ay[3]), pack_b2x4(ay[4], ay[5], ay[6], ay[7]),
+                                  pack_b2x4(ay[8], ay[9], ay[10], ay[11]), pack_b2x4(ay[12], ay[13], ay[14], ay[15])));
+            if (DST == D422) {
+                uint32_t ua[8], va[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { ua[k] = acc_u<SL>(px[2 * k]); va[k] = acc_v<SL>(px[2 * k + 1]); }
+                if (valid) {
+                    stg64(U + (size_t)u * 8, make_uint2(pack_b2x4(ua[0], ua[1], ua[2], ua[3]), pack_b2x4(ua[4], ua[5], ua[6], ua[7])));
+                    stg64(V + (size_t)u * 8, make_uint2(pack_b2x4(va[0], va[1], va[2], va[3]), pack_b2x4(va[4], va[5], va[6], va[7])));
+                }
+            } else if (DST == D411) {
+                uint32_t ua[4], va[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { ua[k] = acc_u<SL>(px[4 * k]); va[k] = acc_v<SL>(px[4 * k + 2]); }
+                if (valid) {
+                    stg32(U + (size_t)u * 4, pack_b2x4(ua[0], ua[1], ua[2], ua[3]));
+                    stg32(V + (size_t)u * 4, pack_b2x4(va[0], va[1], va[2], va[3]));
+                }
+            } else if (DST == D444) {
+                uint32_t ca[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) ca[k] = acc_u<SL>(px[k]);
+                if (valid)
+                    stg128(U + (size_t)u * 16,
+                           make_uint4(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7]),
+                                      pack_b2x4(ca[8], ca[9], ca[10], ca[11]), pack_b2x4(ca[12], ca[13], ca[14], ca[15])));
+#pragma unroll
+                for (int k = 0; k < 16; k++) ca[k] = acc_v<SL>(px[k]);
+                if (valid)
+                    stg128(V + (size_t)u * 16,
+                           make_uint4(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7]),
+                                      pack_b2x4(ca[8], ca[9], ca[10], ca[11]), pack_b2x4(ca[12], ca[13], ca[14], ca[15])));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // launch helpers
 
 inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
@@ -358,6 +588,46 @@ bool fast_yuv2rgb(const ConvertArgs &a, const FastParams &p)
     }
 }
 
+template <int SL, int DST>
+bool launch_rgb2yuv(const FastParams &p, int nframes, cudaStream_t st)
+{
+    LaunchShape s = DST == D420 ? shape_420(p.upr, p.nrp, nframes) : shape_linear(p.nunits, nframes);
+    const size_t smem = (size_t)(s.block.x / 32) * 64 * sizeof(uint4);
+    k_rgb2yuv<SL, DST><<<s.grid, s.block, smem, st>>>(p);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_rgb2yuv");
+    return true;
+}
+
+template <int SL>
+bool dispatch_rgb2yuv_dst(int dstfmt, const FastParams &p, int nframes, cudaStream_t st)
+{
+    switch (dstfmt) {
+    case IMG_YUV420P: return launch_rgb2yuv<SL, D420>(p, nframes, st);
+    case IMG_YUV422P: return launch_rgb2yuv<SL, D422>(p, nframes, st);
+    case IMG_YUV411P: return launch_rgb2yuv<SL, D411>(p, nframes, st);
+    case IMG_YUV444P: return launch_rgb2yuv<SL, D444>(p, nframes, st);
+    case IMG_YUY2:    return launch_rgb2yuv<SL, DYUY2>(p, nframes, st);
+    case IMG_UYVY:    return launch_rgb2yuv<SL, DUYVY>(p, nframes, st);
+    case IMG_YVYU:    return launch_rgb2yuv<SL, DYVYU>(p, nframes, st);
+    case IMG_Y8:      return launch_rgb2yuv<SL, DY8>(p, nframes, st);
+    default: return false;
+    }
+}
+
+bool fast_rgb2yuv(const ConvertArgs &a, const FastParams &p)
+{
+    switch (a.srcfmt) {
+    case IMG_RGB24:  return dispatch_rgb2yuv_dst<L_RGB24>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_BGR24:  return dispatch_rgb2yuv_dst<L_BGR24>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_RGBA32: return dispatch_rgb2yuv_dst<L_RGBA>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_BGRA32: return dispatch_rgb2yuv_dst<L_BGRA>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_ARGB32: return dispatch_rgb2yuv_dst<L_ARGB>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_ABGR32: return dispatch_rgb2yuv_dst<L_ABGR>(a.dstfmt, p, a.nframes, a.stream);
+    default: return false;
+    }
+}
+
 }  // namespace
 
 bool convert_fast(const ConvertArgs &a)
@@ -389,8 +659,12 @@ bool convert_fast(const ConvertArgs &a)
     p.nunits = (uint32_t)(P / 16);
 
     if ((sd.kind == K_PLANAR || sd.kind == K_PACKED) && dd.kind == K_RGB) {
-        if (any420 && p.upr > 1024) return false;
+        if (any420 && p.upr > 256) return false;
         return fast_yuv2rgb(a, p);
+    }
+    if (sd.kind == K_RGB && (dd.kind == K_PLANAR || dd.kind == K_PACKED || dd.kind == K_Y8)) {
+        if (any420 && p.upr > 256) return false;
+        return fast_rgb2yuv(a, p);
     }
     return false;
 }
