@@ -74,6 +74,9 @@ def test_all_pairs_batched_aligned(ac, chk, srcfmt, dstfmt):
             ac.lib.acgpu_force_tier(0)
         assert_same(got[:, :dfb], want, f"batched {F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} tier {tier}")
         assert (got[:, dfb:] == 0x55).all(), "wrote into the inter-frame gap"
+        if tier == 0:
+            # aligned planes + sizes on the 16-pixel grid: every pair must be served by a vectorised tier
+            assert ac.lib.acgpu_last_kernel_tier() >= 2, "fell back to the generic tier"
 
 
 def test_unknown_pairs_and_degenerate_sizes(ac):

@@ -1,0 +1,239 @@
+// fast_common.cuh -- helpers shared by the vectorised-tier translation units (kernels_fast*.cu).
+#pragma once
+
+#include "acgpu_internal.h"
+#include "pixmath.cuh"
+
+namespace acgpu {
+namespace fast {
+
+// ---------------------------------------------------------------------------------------------------
+// Small device helpers
+
+__device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint2 ldg64(const uint8_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
+// streaming stores: the output is never re-read by this kernel
+__device__ __forceinline__ void stg128(uint8_t *p, uint4 v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
+__device__ __forceinline__ void stg64(uint8_t *p, uint2 v) { __stcs(reinterpret_cast<uint2 *>(p), v); }
+__device__ __forceinline__ void stg32(uint8_t *p, uint32_t v) { __stcs(reinterpret_cast<uint32_t *>(p), v); }
+
+__device__ __forceinline__ uint32_t word_of(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int b) { return (w >> (8 * b)) & 0xFFu; }
+
+// One colour channel: j = 16*Y + c (dp4a picks the Y byte and scales it), clamp j to [0, 3498], and the
+// answer is the TOP byte of j*1220944 + 2^23 (pixmath::ylut_word_fast).  3 instructions.
+__device__ __forceinline__ uint32_t channel_word(uint32_t yword, uint32_t ysel, int c)
+{
+    const int j = (int)__dp4a(yword, ysel, (uint32_t)c);
+    const int jc = __vimin_s32_relu(j, pixmath::kJMax);
+    return (uint32_t)jc * pixmath::kJMul + pixmath::kJAdd;
+}
+// (a.b3, b.b3, c.b3, d.b3) -> one word
+__device__ __forceinline__ uint32_t pack_top4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
+}
+
+// Per-warp staging: lane-owned chunks (each lane owns K consecutive 16-byte chunks of the warp's contiguous
+// output) are written to shared memory and read back in global order so every STG covers 512 contiguous bytes.
+// K = 3 needs no swizzle (48-byte lane stride is conflict-free); K = 4 / K = 2 XOR-swizzle the chunk slot.
+template <int K>
+__device__ __forceinline__ int stage_slot(int lane, int k)
+{
+    if (K == 4) return lane * 4 + (k ^ ((lane >> 1) & 3));
+    if (K == 2) return lane * 2 + (k ^ ((lane >> 2) & 1));
+    return lane * K + k;
+}
+template <int K>
+__device__ __forceinline__ int stage_slot_linear(int c)   // c = global chunk index inside the warp tile
+{
+    return stage_slot<K>(c / K, c % K);
+}
+
+enum SrcKind { S420 = 0, S422 = 1, S411 = 2, S444 = 3, SYUY2 = 4, SUYVY = 5, SYVYU = 6 };
+
+struct FastParams {
+    const uint8_t *s0, *s1, *s2;
+    uint8_t *d0, *d1, *d2;
+    size_t spitch, dpitch;
+    int w, h;
+    int upr;           // 4:2:0 mode: 16-pixel units per row
+    int nrp;           // 4:2:0 mode: row pairs
+    uint32_t nunits;   // linear mode: units per frame
+};
+
+// (a.b2, b.b2, c.b2, d.b2) -> one word
+__device__ __forceinline__ uint32_t pack_b2x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0062), __byte_perm(c, d, 0x0062), 0x5410);
+}
+
+// Stores K lane-owned 16-byte chunks (words ow[0..4K)) through the staging buffer; plain coalesced write.
+template <int K>
+__device__ __forceinline__ void store_chunks(uint4 *stage, int lane, const uint32_t *ow, uint8_t *warpbase, int nvalid)
+{
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        stage[stage_slot<K>(lane, k)] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+    __syncwarp();
+    const int nchunks = nvalid * K;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const int c = j * 32 + lane;
+        if (c < nchunks) stg128(warpbase + (size_t)c * 16, stage[stage_slot_linear<K>(c)]);
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+
+inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+struct LaunchShape {
+    dim3 grid, block;
+};
+
+// 4:2:0 mode: one block spans a row pair (ceil(upr/32) warps), grid.x strides over row pairs.
+inline LaunchShape shape_420(int upr, int nrp, int nframes)
+{
+    LaunchShape s;
+    const int threads = ((upr + 31) / 32) * 32;
+    s.block = dim3(threads);
+    const int per_sm = 2048 / threads;
+    long want = (long)sm_count() * per_sm * 2;              // about two waves of resident blocks
+    long gx = (want + nframes - 1) / nframes;
+    if (gx < 1) gx = 1;
+    if (gx > nrp) gx = nrp;
+    s.grid = dim3((unsigned)gx, (unsigned)nframes);
+    return s;
+}
+
+inline LaunchShape shape_linear(uint32_t nunits, int nframes)
+{
+    LaunchShape s;
+    s.block = dim3(256);
+    long want = (long)sm_count() * 8 * 2;
+    long gx = (want + nframes - 1) / nframes;
+    const long maxgx = (nunits + 255) / 256;
+    if (gx < 1) gx = 1;
+    if (gx > maxgx) gx = maxgx;
+    s.grid = dim3((unsigned)gx, (unsigned)nframes);
+    return s;
+}
+
+
+// Writes one row's 16 pixels per lane (BPP*4 words) through the warp staging buffer to `rowbase`
+// (the address of the warp's first unit).  nvalid = number of lanes holding real units (warp-uniform).
+template <int BPP, bool AFIRST>
+__device__ __forceinline__ void store_row_rgb(uint4 *stage, int lane, const uint32_t *ow, uint8_t *rowbase, int nvalid)
+{
+    constexpr int K = BPP;   // 16-byte chunks per lane
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        stage[stage_slot<K>(lane, k)] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+    __syncwarp();
+    const int nchunks = nvalid * K;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const int c = j * 32 + lane;
+        if (c < nchunks) {
+            uint4 v = stage[stage_slot_linear<K>(c)];
+            uint8_t *g = rowbase + (size_t)c * 16;
+            if (BPP == 4) {     // keep the destination's alpha bytes (img_yuv_rgb.c:62-64 never stores them)
+                const uint4 old = *reinterpret_cast<const uint4 *>(g);
+                const uint32_t m = AFIRST ? 0x000000FFu : 0xFF000000u;
+                v.x = (v.x & ~m) | (old.x & m);
+                v.y = (v.y & ~m) | (old.y & m);
+                v.z = (v.z & ~m) | (old.z & m);
+                v.w = (v.w & ~m) | (old.w & m);
+            }
+            stg128(g, v);
+        }
+    }
+    __syncwarp();
+}
+
+enum RgbLayout { L_RGB24 = 0, L_BGR24 = 1, L_RGBA = 2, L_BGRA = 3, L_ARGB = 4, L_ABGR = 5 };
+enum YuvDst { D420 = 0, D422 = 1, D411 = 2, D444 = 3, DYUY2 = 4, DUYVY = 5, DYVYU = 6, DY8 = 7 };
+
+template <int SL> struct RgbInfo {
+    static constexpr int bpp = SL <= L_BGR24 ? 3 : 4;
+    // byte position of each channel inside the (normalised) pixel word
+    static constexpr int rpos = (SL == L_RGB24 || SL == L_RGBA) ? 0 : (SL == L_BGR24 || SL == L_BGRA) ? 2 : SL == L_ARGB ? 1 : 3;
+    static constexpr int gpos = (SL == L_ARGB || SL == L_ABGR) ? 2 : 1;
+    static constexpr int bpos = (SL == L_RGB24 || SL == L_RGBA) ? 2 : (SL == L_BGR24 || SL == L_BGRA) ? 0 : SL == L_ARGB ? 3 : 1;
+    static constexpr uint32_t half(int kr, int kg, int kb, int p0)   // coefficients for byte positions p0, p0+1
+    {
+        const int c0 = rpos == p0 ? kr : gpos == p0 ? kg : bpos == p0 ? kb : 0;
+        const int c1 = rpos == p0 + 1 ? kr : gpos == p0 + 1 ? kg : bpos == p0 + 1 ? kb : 0;
+        return (uint32_t)(c0 & 0xFFFF) | ((uint32_t)(c1 & 0xFFFF) << 16);
+    }
+};
+
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_lo_su(uint32_t a, uint32_t b, uint32_t c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_su(uint32_t a, uint32_t b, uint32_t c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
+}
+
+// Loads the 16 pixels of unit `u` of a row that starts at `row` into normalised pixel words.
+template <int SL>
+__device__ __forceinline__ void load_rgb16(const uint8_t *row, uint32_t u, bool valid, uint32_t *px)
+{
+    if (RgbInfo<SL>::bpp == 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) v = ldg128(row + (size_t)u * 64 + k * 16);
+            px[4 * k] = v.x; px[4 * k + 1] = v.y; px[4 * k + 2] = v.z; px[4 * k + 3] = v.w;
+        }
+    } else {
+        uint32_t w[12];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) v = ldg128(row + (size_t)u * 48 + k * 16);
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {   // 4 pixels = 3 words
+            px[4 * g + 0] = w[3 * g];
+            px[4 * g + 1] = __byte_perm(w[3 * g], w[3 * g + 1], 0x0543);
+            px[4 * g + 2] = __byte_perm(w[3 * g + 1], w[3 * g + 2], 0x0432);
+            px[4 * g + 3] = w[3 * g + 2] >> 8;
+        }
+    }
+}
+
+// per-byte rounded-up / truncated means on four packed bytes (aclib (a+b+1)/2 and (a+b)/2)
+__device__ __forceinline__ uint32_t avg_up4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7F7F7F7Fu); }
+__device__ __forceinline__ uint32_t avg_dn4(uint32_t a, uint32_t b) { return (a & b) + (((a ^ b) >> 1) & 0x7F7F7F7Fu); }
+
+}  // namespace fast
+
+// family entry points (each returns false without launching when the pair is not one of its own)
+bool fast_yuv_family(const ConvertArgs &a, const fast::FastParams &p);   // kernels_fast_yuv.cu: YUV<->YUV, Y8, gray maps
+bool fast_rgb_family(const ConvertArgs &a, const fast::FastParams &p);   // kernels_fast_rgb.cu: RGB<->RGB, gray<->RGB, Y8->RGB
+
+}  // namespace acgpu

@@ -69,6 +69,17 @@ PM_HD int y2gray(int i) { return i <= 16 ? 0 : i >= 235 ? 255 : (i - 16) * 255 /
 PM_HD int gray2y(int i) { return 16 + i * 219 / 255; }
 PM_HD int rgb2gray(int r, int g, int b) { return (19595 * r + 38470 * g + 7471 * b + 32768) >> 16; }
 
+// Reduced forms: both maps are a clamp plus ONE multiply whose TOP BYTE is the answer.
+//   floor(x*255/219) == (x*19535115) >> 24 for x in [0,219];  floor(i*219/255) == (i*14408668) >> 24 for i in [0,255]
+constexpr uint32_t kY2GrayMul = 19535115u, kGray2YMul = 14408668u;
+PM_HD uint32_t y2gray_word_fast(int i)     // answer in bits 31..24
+{
+    int x = i - 16;
+    x = x < 0 ? 0 : x > 219 ? 219 : x;
+    return (uint32_t)x * kY2GrayMul;
+}
+PM_HD uint32_t gray2y_word_fast(int i) { return (uint32_t)i * kGray2YMul + (16u << 24); }
+
 // ---- blends (aclib/average.c:37-38, aclib/rescale.c:44-45) ---------------------------------------
 PM_HD int avg2(int a, int b) { return (a + b + 1) / 2; }
 PM_HD int avg2_trunc(int a, int b) { return (a + b) / 2; }           // aclib/img_yuv_mixed.c:135,137
