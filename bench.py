@@ -98,6 +98,62 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+class Dist:
+    """torch.distributed plumbing for the multi-rank bench: barrier, max / sum over ranks.  The data path has no
+    collective (frames are independent); this only synchronises the timed region and reduces the timing scalar.
+    backend "nccl" on GPUs; "gloo" is used by the CPU tests (tests/test_bench_dist.py)."""
+
+    def __init__(self, backend: str = "nccl"):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.backend = backend
+        self.dist = None
+        self.torch = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group(backend)
+
+    def _tensor(self, v, dtype):
+        dev = "cuda" if self.backend == "nccl" else "cpu"
+        return self.torch.tensor([v], device=dev, dtype=dtype)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            if self.backend == "nccl":
+                self.torch.cuda.synchronize()
+
+    def max_float(self, v: float) -> float:
+        if self.dist is None:
+            return v
+        t = self._tensor(v, self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_int(self, v: int) -> int:
+        if self.dist is None:
+            return v
+        t = self._tensor(v, self.torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def aggregate_value(units_all_ranks: int, steps: int, ms_max: float) -> float:
+    """Whole-job throughput: units every rank processed / the slowest rank's device time."""
+    return units_all_ranks * steps / (ms_max / 1000.0)
+
+
 def cpubench(lib: str, accel: int, threads: int, seconds: float, kind: str, a: int, b: int, w: int, h: int, oracle=False):
     exe = os.path.join(ROOT, "oracle", "cpubench")
     if kind == "convert":
@@ -129,14 +185,15 @@ def workload_bytes(kind, a, b, w, h):
     """Algorithmic bytes per frame."""
     if kind == "convert":
         return F.algorithmic_bytes(a, b, w, h)
+    # frame-granular row shapes: unique bytes touched by ONE fused pass (source rows read once + rows written),
+    # not aclib's per-call 3 B per blended byte -- the fused kernel gets the row reuse from cache.
     bpl = w * a
     if kind == "deint":
-        if b == 0:   # interpolate: even rows copied (1+1 B/B), odd rows averaged (2+1 B/B), last odd row copied
-            odd_avg = (h - 1) // 2 if h % 2 == 0 else h // 2
-            return bpl * (odd_avg * 3 + (h - odd_avg) * 2)
-        return bpl * ((h - 2) * 4 + 2 * 3)   # linear blend fused: 3 rows read + 1 written (2+1 for the edge rows)
+        if b == 0:   # interpolate reads only the even rows (tcvideo.c:353-364)
+            return bpl * ((h + 1) // 2 + h)
+        return bpl * (h + h)                 # linear blend reads every row once
     new_h = h * 2 // 3
-    return bpl * new_h * 3                   # resize 3:2 shrink: every output row blends two source rows
+    return bpl * (h + new_h)                 # 3:2 shrink touches every source row
 
 
 def run_reference(args, kind, a, b, w, h, name):
@@ -178,6 +235,9 @@ def main():
     ap.add_argument("--tier", type=int, default=0, help="force a kernel tier (profiling)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="process-group backend (gloo: CPU tests)")
+    ap.add_argument("--dry-run", action="store_true",
+                    help="exercise the multi-rank plumbing with no GPU work (tests/test_bench_dist.py); not a measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "acgpu":
         args.warmup = 3
@@ -190,15 +250,21 @@ def main():
         run_reference(args, kind, a, b, w, h, name)
         return
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dc = Dist(args.backend)
+    rank, local_rank, world = dc.rank, dc.local_rank, dc.world
+    abytes = workload_bytes(kind, a, b, w, h)
+
+    if args.dry_run:
+        # no device: each rank pretends its steps took (rank+1) ms so the max-over-ranks path is observable
+        dc.barrier()
+        ms = dc.max_float(float(rank + 1) * args.steps)
+        total_units = dc.sum_int(batch)
+        dc.barrier()
+        if rank == 0:
+            print(json.dumps({"dry_run": True, "n_gpus": world, "steps": args.steps, "ms_max": ms,
+                              "units_all_ranks": total_units, "value": aggregate_value(total_units, args.steps, ms)}), flush=True)
+        dc.close()
+        return
 
     import numpy as np
     ac = pkg.AcGpu()
@@ -239,10 +305,7 @@ def main():
 
     def barrier():
         ac.sync(stream)
-        if dist is not None:
-            dist.barrier()
-            import torch
-            torch.cuda.synchronize()
+        dc.barrier()
 
     for _ in range(args.warmup):
         step()
@@ -258,9 +321,9 @@ def main():
     lib.acgpu_event_record(e1, stream)
     ac.sync(stream)
     launches = int(lib.acgpu_launch_count(0))
-    ms = float(lib.acgpu_event_elapsed_ms(e0, e1))
+    ms_local = float(lib.acgpu_event_elapsed_ms(e0, e1))
     # keep the GPU busy a little longer if the region was too short for the 100 ms clock sampler
-    t_end = time.time() + max(0.0, 0.5 - ms / 1000.0)
+    t_end = time.time() + max(0.0, 0.5 - ms_local / 1000.0)
     while time.time() < t_end:
         step()
     ac.sync(stream)
@@ -268,11 +331,8 @@ def main():
     sampler.join()
     barrier()
     tier = lib.acgpu_last_kernel_tier()
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = dc.max_float(ms_local)
+    total_units = dc.sum_int(batch)
 
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------------------
     e2e = None
@@ -283,42 +343,36 @@ def main():
             hs.array[i * sfb:(i + 1) * sfb] = host[i % uniq]
         for _ in range(2):
             ac._ok(lib.acgpu_imgconvert_frames_host(hs.ptr, a, hd.ptr, b, w, h, eb))
-        if dist is not None:
-            dist.barrier()
+        dc.barrier()
         esteps = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(esteps):
             ac._ok(lib.acgpu_imgconvert_frames_host(hs.ptr, a, hd.ptr, b, w, h, eb))
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            import torch
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = dc.max_float(time.perf_counter() - t0)
         e2e = {"value": round(world * eb * esteps / dt, 2), "unit": "frames/s", "h2d_bytes_per_step": eb * sfb,
                "d2h_bytes_per_step": eb * dfb, "frames_per_step": eb, "steps": esteps,
                "pcie_gbs_d2h": round(world * eb * esteps * dfb / dt / 1e9, 2),
-               "note": "acgpu_imgconvert_frames_host on pinned host buffers; wall clock around the synchronous call"}
+               "note": "acgpu_imgconvert_frames_host on pinned host buffers; wall clock around the synchronous call, max over ranks"}
         hs.free(); hd.free()
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        dc.close()
         return
 
     peak, peak_src = read_peaks()
-    abytes = workload_bytes(kind, a, b, w, h)
     launches_per_step = max(1, launches // max(1, args.steps))
-    gbs = batch * abytes * args.steps / (ms / 1000.0) / 1e9            # this rank's kernel(s)
+    gbs = batch * abytes * args.steps / (ms_local / 1000.0) / 1e9            # rank 0's kernel(s)
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(name, {}).get("dram_bytes_per_launch")
+            t = json.load(f).get(name)
+        if t:
+            traffic = int(t["dram_bytes_per_launch"] * batch / t["frames_per_launch"] / launches_per_step)
     except Exception:
         pass
     line = {
         "metric": METRIC.get(name, name + " frames/s"),
-        "value": round(world * batch * args.steps / (ms / 1000.0), 1), "unit": "frames/s",
+        "value": round(aggregate_value(total_units, args.steps, ms), 1), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": name, "width": w, "height": h, "frames_per_step_per_gpu": batch,
@@ -349,8 +403,7 @@ def main():
             "c_path_1_thread": round(res[("c", 1)], 2),
         }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    dc.close()
 
 
 if __name__ == "__main__":
