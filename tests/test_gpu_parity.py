@@ -66,7 +66,7 @@ def test_all_pairs_batched_aligned(ac, chk, srcfmt, dstfmt):
     frames = np.stack([ck.random_frame(srcfmt, w, h, seed=20 + i) for i in range(nf)])
     dfb = F.frame_bytes(dstfmt, w, h)
     want = np.stack([chk.convert(frames[i], srcfmt, dstfmt, w, h, pad=0)[1] for i in range(nf)])
-    for tier in (0, 1):
+    for tier in (0, 1, 2):
         ac.lib.acgpu_force_tier(tier)
         try:
             got = ac.convert_batch(frames, srcfmt, dstfmt, w, h, dst_pitch=dfb + 256)

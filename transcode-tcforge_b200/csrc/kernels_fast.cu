@@ -96,6 +96,32 @@ __device__ __forceinline__ void convert_row(const uint32_t *yw, const int *cr, c
     }
 }
 
+// ---- bulk (TMA) store of a warp tile: shared -> global in one instruction, issued by lane 0 ------------------
+// The lane-owned chunks are written to shared memory in plain global order (a 48-byte lane stride is bank-conflict
+// free), made visible to the async proxy, and the whole 1536-byte tile leaves with one cp.async.bulk (SASS UBLKCP):
+// no LDS read-back, no per-lane STG, no store address arithmetic.  Two buffers per warp alternate so the copy engine
+// drains one tile while the warp computes the next.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K>
+__device__ __forceinline__ void store_row_bulk(uint4 *buf, int lane, const uint32_t *ow, uint8_t *gdst, int nvalid)
+{
+    if (lane == 0) bulk_wait_read<1>();      // this buffer's previous tile has been read out (the other may be in flight)
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; k++) buf[lane * K + k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) bulk_store(gdst, buf, (uint32_t)nvalid * K * 16);
+}
+
 template <int SRC>
 __device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32_t V, int &cr, int &cg, int &cb)
 {
@@ -105,16 +131,19 @@ __device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32
     cb = tu.x;
 }
 
-template <int SRC, bool SWAP, int BPP, bool AFIRST>
+template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK>
 __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
 {
+    static_assert(!BULK || BPP == 3, "bulk stores cannot merge the untouched alpha byte");
     using SI = SrcInfo<SRC>;
     __shared__ int2 s_tab[512];
     extern __shared__ uint4 s_stage[];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 *stage = s_stage + warp * (32 * BPP);
+    uint4 *stage = s_stage + warp * (32 * BPP) * (BULK ? 2 : 1);
+    uint4 *stage2 = stage + 32 * BPP;      // BULK: second tile buffer
+    (void)stage2;
     const size_t soff = (size_t)blockIdx.y * p.spitch, doff = (size_t)blockIdx.y * p.dpitch;
     uint8_t *dst = p.d0 + doff;
 
@@ -143,13 +172,17 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
             uint32_t ow[BPP * 4];
             uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + warp * 512) * BPP;
             convert_row<SRC, SWAP, BPP, AFIRST>(y0, cr, cg, cb, ow);
-            store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0, nvalid);
+            if (BULK) store_row_bulk<BPP>(stage, lane, ow, row0, nvalid);
+            else store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0, nvalid);
             convert_row<SRC, SWAP, BPP, AFIRST>(y1, cr, cg, cb, ow);
-            store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+            if (BULK) store_row_bulk<BPP>(stage2, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+            else store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
         }
+        if (BULK && lane == 0) bulk_wait_all<0>();
     } else {
         const uint8_t *S0 = p.s0 + soff, *S1 = p.s1 + soff, *S2 = p.s2 + soff;
         const uint32_t stride = gridDim.x * blockDim.x;
+        bool flip = false;
         for (uint32_t base = blockIdx.x * blockDim.x; base < p.nunits; base += stride) {
             const uint32_t u = base + threadIdx.x;
             const uint32_t warp_u0 = base + warp * 32;
@@ -191,8 +224,14 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
             }
             uint32_t ow[BPP * 4];
             convert_row<SRC, SWAP, BPP, AFIRST>(yw, cr, cg, cb, ow);
-            store_row_rgb<BPP, AFIRST>(stage, lane, ow, dst + (size_t)warp_u0 * 16 * BPP, nvalid);
+            if (BULK) {
+                store_row_bulk<BPP>(flip ? stage2 : stage, lane, ow, dst + (size_t)warp_u0 * 16 * BPP, nvalid);
+                flip = !flip;
+            } else {
+                store_row_rgb<BPP, AFIRST>(stage, lane, ow, dst + (size_t)warp_u0 * 16 * BPP, nvalid);
+            }
         }
+        if (BULK && lane == 0) bulk_wait_all<0>();
     }
 }
 
@@ -332,12 +371,12 @@ __global__ void __launch_bounds__(256, 4) k_rgb2yuv(FastParams p)
     }
 }
 
-template <int SRC, bool SWAP, int BPP, bool AFIRST>
+template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK = false>
 bool launch_yuv2rgb(const FastParams &p, int nframes, cudaStream_t st)
 {
     LaunchShape s = SRC == S420 ? shape_420(p.upr, p.nrp, nframes) : shape_linear(p.nunits, nframes);
-    const size_t smem = (size_t)(s.block.x / 32) * 32 * BPP * sizeof(uint4);
-    k_yuv2rgb<SRC, SWAP, BPP, AFIRST><<<s.grid, s.block, smem, st>>>(p);
+    const size_t smem = (size_t)(s.block.x / 32) * 32 * BPP * sizeof(uint4) * (BULK ? 2 : 1);
+    k_yuv2rgb<SRC, SWAP, BPP, AFIRST, BULK><<<s.grid, s.block, smem, st>>>(p);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_yuv2rgb");
     return true;
@@ -353,6 +392,16 @@ bool dispatch_yuv2rgb_dst(int dstfmt, const FastParams &p, int nframes, cudaStre
     case IMG_BGRA32: return launch_yuv2rgb<SRC, true, 4, false>(p, nframes, st);
     case IMG_ARGB32: return launch_yuv2rgb<SRC, false, 4, true>(p, nframes, st);
     case IMG_ABGR32: return launch_yuv2rgb<SRC, true, 4, true>(p, nframes, st);
+    default: return false;
+    }
+}
+
+template <int SRC>
+bool dispatch_yuv2rgb_bulk(int dstfmt, const FastParams &p, int nframes, cudaStream_t st)
+{
+    switch (dstfmt) {
+    case IMG_RGB24: return launch_yuv2rgb<SRC, false, 3, false, true>(p, nframes, st);
+    case IMG_BGR24: return launch_yuv2rgb<SRC, true, 3, false, true>(p, nframes, st);
     default: return false;
     }
 }
@@ -413,26 +462,25 @@ bool fast_rgb2yuv(const ConvertArgs &a, const FastParams &p)
 
 }  // namespace
 
-bool convert_fast(const ConvertArgs &a)
+// Builds the launch parameters if the call is inside the vectorised tiers' domain.
+static bool fast_domain(const ConvertArgs &a, FastParams *out)
 {
     const FmtDesc sd = describe(a.srcfmt), dd = describe(a.dstfmt);
     const int w = a.w, h = a.h;
     if (w <= 0 || h <= 0 || a.nframes <= 0) return false;
-    // alignment domain
     for (int i = 0; i < 3; i++)
         if ((a.src.p[i] && !al16(a.src.p[i])) || (a.dst.p[i] && !al16(a.dst.p[i]))) return false;
     if (a.nframes > 1 && (a.src.pitch % 16 || a.dst.pitch % 16)) return false;
     const bool any420 = a.srcfmt == IMG_YUV420P || a.dstfmt == IMG_YUV420P;
     const size_t P = (size_t)w * h;
     if (any420) {
-        if (w % 16 || h % 2) return false;
+        if (w % 16 || h % 2 || w / 16 > 256) return false;
     } else {
         if (P % 16) return false;
         if ((a.srcfmt == IMG_YUV411P || a.dstfmt == IMG_YUV411P) && w % 4) return false;
         if ((sd.kind == K_PACKED || dd.kind == K_PACKED || a.srcfmt == IMG_YUV422P || a.dstfmt == IMG_YUV422P) && w % 2) return false;
     }
     if (P / 16 > 0x7FFFFFFFu) return false;
-
     FastParams p{};
     p.s0 = a.src.p[0]; p.s1 = a.src.p[1]; p.s2 = a.src.p[2];
     p.d0 = a.dst.p[0]; p.d1 = a.dst.p[1]; p.d2 = a.dst.p[2];
@@ -440,20 +488,39 @@ bool convert_fast(const ConvertArgs &a)
     p.w = w; p.h = h;
     p.upr = w / 16; p.nrp = h / 2;
     p.nunits = (uint32_t)(P / 16);
+    *out = p;
+    return true;
+}
 
-    if ((sd.kind == K_PLANAR || sd.kind == K_PACKED) && dd.kind == K_RGB) {
-        if (any420 && p.upr > 256) return false;
-        return fast_yuv2rgb(a, p);
-    }
-    if (sd.kind == K_RGB && (dd.kind == K_PLANAR || dd.kind == K_PACKED || dd.kind == K_Y8)) {
-        if (any420 && p.upr > 256) return false;
-        return fast_rgb2yuv(a, p);
-    }
-    if (any420 && p.upr > 256) return false;
+bool convert_fast(const ConvertArgs &a)
+{
+    FastParams p;
+    if (!fast_domain(a, &p)) return false;
+    const FmtDesc sd = describe(a.srcfmt), dd = describe(a.dstfmt);
+    if ((sd.kind == K_PLANAR || sd.kind == K_PACKED) && dd.kind == K_RGB) return fast_yuv2rgb(a, p);
+    if (sd.kind == K_RGB && (dd.kind == K_PLANAR || dd.kind == K_PACKED || dd.kind == K_Y8)) return fast_rgb2yuv(a, p);
     const bool s_yuvish = sd.kind == K_PLANAR || sd.kind == K_PACKED || sd.kind == K_Y8 || sd.kind == K_GRAY;
     const bool d_yuvish = dd.kind == K_PLANAR || dd.kind == K_PACKED || dd.kind == K_Y8 || dd.kind == K_GRAY;
     if (s_yuvish && d_yuvish) return fast_yuv_family(a, p);
     return fast_rgb_family(a, p);
+}
+
+// Tier 3: the same arithmetic, but 24-bit RGB tiles leave shared memory through bulk (TMA) stores.
+bool convert_tma(const ConvertArgs &a)
+{
+    if (a.dstfmt != IMG_RGB24 && a.dstfmt != IMG_BGR24) return false;
+    FastParams p;
+    if (!fast_domain(a, &p)) return false;
+    switch (a.srcfmt) {
+    case IMG_YUV420P: return dispatch_yuv2rgb_bulk<S420>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV422P: return dispatch_yuv2rgb_bulk<S422>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV411P: return dispatch_yuv2rgb_bulk<S411>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV444P: return dispatch_yuv2rgb_bulk<S444>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUY2:    return dispatch_yuv2rgb_bulk<SYUY2>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_UYVY:    return dispatch_yuv2rgb_bulk<SUYVY>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YVYU:    return dispatch_yuv2rgb_bulk<SYVYU>(a.dstfmt, p, a.nframes, a.stream);
+    default: return false;
+    }
 }
 
 }  // namespace acgpu
