@@ -23,10 +23,12 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w, int b) { return (w >> (8
 
 // One colour channel: j = 16*Y + c (dp4a picks the Y byte and scales it), clamp j to [0, 3498], and the
 // answer is the TOP byte of j*1220944 + 2^23 (pixmath::ylut_word_fast).  3 instructions.
+// BIAS: a constant the caller left inside c (biased table entries); it is removed inside the clamp instruction.
+template <int BIAS>
 __device__ __forceinline__ uint32_t channel_word(uint32_t yword, uint32_t ysel, int c)
 {
     const int j = (int)__dp4a(yword, ysel, (uint32_t)c);
-    const int jc = __vimin_s32_relu(j, pixmath::kJMax);
+    const int jc = BIAS ? __viaddmin_s32_relu(j, -BIAS, pixmath::kJMax) : __vimin_s32_relu(j, pixmath::kJMax);
     return (uint32_t)jc * pixmath::kJMul + pixmath::kJAdd;
 }
 // (a.b3, b.b3, c.b3, d.b3) -> one word

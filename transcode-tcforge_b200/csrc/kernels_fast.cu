@@ -43,6 +43,29 @@ constexpr ChromaTabs make_tabs()
 }
 __device__ const ChromaTabs g_tabs = make_tabs();
 
+// Same terms packed two per 32-bit word and biased by +4096 so both halves are non-negative:
+//   v16[i] = (rV-256+4096) | (gV-256+4096) << 16,  u16[i] = (bU-256+4096) | (gU+4096) << 16.
+// One LDS.32 per table (32 banks -> ~1.7x fewer conflict replays on random chroma than LDS.64); the biases are
+// removed for free inside the clamp instruction (VIADDMNMX: relu(min(j - bias, 3498))).
+struct ChromaTabs16 {
+    uint32_t v[256];
+    uint32_t u[256];
+};
+constexpr ChromaTabs16 make_tabs16()
+{
+    ChromaTabs16 t{};
+    for (int i = 0; i < 256; i++) {
+        t.v[i] = (uint32_t)(chroma_term(pixmath::kCRV, i) - 256 + 4096) | ((uint32_t)(chroma_term(pixmath::kCGV, i) - 256 + 4096) << 16);
+        t.u[i] = (uint32_t)(chroma_term(pixmath::kCBU, i) - 256 + 4096) | ((uint32_t)(chroma_term(pixmath::kCGU, i) + 4096) << 16);
+    }
+    return t;
+}
+__device__ const ChromaTabs16 g_tabs16 = make_tabs16();
+#ifndef ACGPU_LUT16
+#define ACGPU_LUT16 1
+#endif
+constexpr int kBiasRB = ACGPU_LUT16 ? 4096 : 0, kBiasG = ACGPU_LUT16 ? 8192 : 0;
+
 // ---------------------------------------------------------------------------------------------------
 // K1: YUV (7 layouts) -> RGB (6 layouts).  aclib/img_yuv_rgb.c:58-136.
 //   SWAP   : first colour byte is B instead of R (BGR24, BGRA32, ABGR32)
@@ -78,9 +101,9 @@ __device__ __forceinline__ void convert_row(const uint32_t *yw, const int *cr, c
                 word = yw[g];
                 sel = 0x10u << (8 * k);
             }
-            xa[k] = channel_word(word, sel, SWAP ? cb[s] : cr[s]);
-            xg[k] = channel_word(word, sel, cg[s]);
-            xc[k] = channel_word(word, sel, SWAP ? cr[s] : cb[s]);
+            xa[k] = channel_word<kBiasRB>(word, sel, SWAP ? cb[s] : cr[s]);
+            xg[k] = channel_word<kBiasG>(word, sel, cg[s]);
+            xc[k] = channel_word<kBiasRB>(word, sel, SWAP ? cr[s] : cb[s]);
         }
         if (BPP == 3) {
             out[g * 3 + 0] = pack_top4(xa[0], xg[0], xc[0], xa[1]);
@@ -125,10 +148,18 @@ __device__ __forceinline__ void store_row_bulk(uint4 *buf, int lane, const uint3
 template <int SRC>
 __device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32_t V, int &cr, int &cg, int &cb)
 {
+#if ACGPU_LUT16
+    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tab);
+    const uint32_t tv = t32[V], tu = t32[256 + U];
+    cr = (int)(tv & 0xFFFFu);
+    cb = (int)(tu & 0xFFFFu);
+    cg = (int)((tv >> 16) + (tu >> 16));
+#else
     const int2 tv = tab[V], tu = tab[256 + U];
     cr = tv.x;
     cg = tv.y + tu.y;
     cb = tu.x;
+#endif
 }
 
 template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK>
@@ -138,7 +169,11 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
     using SI = SrcInfo<SRC>;
     __shared__ int2 s_tab[512];
     extern __shared__ uint4 s_stage[];
+#if ACGPU_LUT16
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs16)[i];
+#else
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs)[i];
+#endif
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *stage = s_stage + warp * (32 * BPP) * (BULK ? 2 : 1);
