@@ -4,6 +4,8 @@
 #include "acgpu_internal.h"
 #include "pixmath.cuh"
 
+#include <stdlib.h>
+
 namespace acgpu {
 namespace fast {
 
@@ -91,6 +93,17 @@ __device__ __forceinline__ void store_chunks(uint4 *stage, int lane, const uint3
 // ---------------------------------------------------------------------------------------------------
 // launch helpers
 
+// How many "waves" of resident blocks a launch is cut into.  Measured on B200 (tools/membench, profiles/): a grid of
+// exactly-resident persistent blocks loses ~10 % of HBM bandwidth to static load imbalance between SMs (two dies,
+// near/far L2); the block scheduler evens that out when there are many more blocks than slots.  Kernels without a
+// per-block prologue want ~32 waves, the YUV->RGB kernels (2 KB table fill per block) peak at ~8.
+inline int waves(int dflt)
+{
+    static int v = -2;
+    if (v == -2) { const char *e = getenv("ACGPU_WAVES"); v = e ? atoi(e) : -1; }
+    return v > 0 ? v : dflt;
+}
+
 inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 struct LaunchShape {
@@ -98,13 +111,13 @@ struct LaunchShape {
 };
 
 // 4:2:0 mode: one block spans a row pair (ceil(upr/32) warps), grid.x strides over row pairs.
-inline LaunchShape shape_420(int upr, int nrp, int nframes)
+inline LaunchShape shape_420(int upr, int nrp, int nframes, int nwaves = 32)
 {
     LaunchShape s;
     const int threads = ((upr + 31) / 32) * 32;
     s.block = dim3(threads);
     const int per_sm = 2048 / threads;
-    long want = (long)sm_count() * per_sm * 2;              // about two waves of resident blocks
+    long want = (long)sm_count() * per_sm * waves(nwaves);
     long gx = (want + nframes - 1) / nframes;
     if (gx < 1) gx = 1;
     if (gx > nrp) gx = nrp;
@@ -112,11 +125,11 @@ inline LaunchShape shape_420(int upr, int nrp, int nframes)
     return s;
 }
 
-inline LaunchShape shape_linear(uint32_t nunits, int nframes)
+inline LaunchShape shape_linear(uint32_t nunits, int nframes, int nwaves = 32)
 {
     LaunchShape s;
     s.block = dim3(256);
-    long want = (long)sm_count() * 8 * 2;
+    long want = (long)sm_count() * 8 * waves(nwaves);
     long gx = (want + nframes - 1) / nframes;
     const long maxgx = (nunits + 255) / 256;
     if (gx < 1) gx = 1;

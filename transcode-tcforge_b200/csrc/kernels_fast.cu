@@ -145,6 +145,19 @@ __device__ __forceinline__ void store_row_bulk(uint4 *buf, int lane, const uint3
     if (lane == 0) bulk_store(gdst, buf, (uint32_t)nvalid * K * 16);
 }
 
+// 32-bit destinations are read-modify-written (alpha is kept).  Asking L2 for the destination tile at the top of
+// the iteration takes the DRAM read latency off the critical path between "pixels ready" and "store".
+template <int BPP>
+__device__ __forceinline__ void prefetch_dest_row(const uint8_t *rowbase, int lane, int nvalid)
+{
+    if (BPP != 4) return;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = j * 32 + lane;
+        if (c < nvalid * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowbase + (size_t)c * 16));
+    }
+}
+
 template <int SRC>
 __device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32_t V, int &cr, int &cg, int &cb)
 {
@@ -200,12 +213,14 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
                 uu = ldg64(U + co);
                 vv = ldg64(V + co);
             }
+            uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + warp * 512) * BPP;
+            prefetch_dest_row<BPP>(row0, lane, nvalid);
+            prefetch_dest_row<BPP>(row0 + (size_t)p.w * BPP, lane, nvalid);
             int cr[8], cg[8], cb[8];
 #pragma unroll
             for (int s = 0; s < 8; s++)
                 chroma_terms<SRC>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
             uint32_t ow[BPP * 4];
-            uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + warp * 512) * BPP;
             convert_row<SRC, SWAP, BPP, AFIRST>(y0, cr, cg, cb, ow);
             if (BULK) store_row_bulk<BPP>(stage, lane, ow, row0, nvalid);
             else store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0, nvalid);
@@ -224,6 +239,7 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
             if (warp_u0 >= p.nunits) break;                  // warp-uniform
             const int nvalid = (int)min(32u, p.nunits - warp_u0);
             const bool valid = u < p.nunits;
+            prefetch_dest_row<BPP>(dst + (size_t)warp_u0 * 16 * BPP, lane, nvalid);
             uint32_t yw[SI::packed ? 8 : 4];
             int cr[SI::nchroma], cg[SI::nchroma], cb[SI::nchroma];
             if (SI::packed) {
@@ -409,7 +425,7 @@ __global__ void __launch_bounds__(256, 4) k_rgb2yuv(FastParams p)
 template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK = false>
 bool launch_yuv2rgb(const FastParams &p, int nframes, cudaStream_t st)
 {
-    LaunchShape s = SRC == S420 ? shape_420(p.upr, p.nrp, nframes) : shape_linear(p.nunits, nframes);
+    LaunchShape s = SRC == S420 ? shape_420(p.upr, p.nrp, nframes, 8) : shape_linear(p.nunits, nframes, 8);
     const size_t smem = (size_t)(s.block.x / 32) * 32 * BPP * sizeof(uint4) * (BULK ? 2 : 1);
     k_yuv2rgb<SRC, SWAP, BPP, AFIRST, BULK><<<s.grid, s.block, smem, st>>>(p);
     note_launch();

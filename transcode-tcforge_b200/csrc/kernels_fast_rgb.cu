@@ -128,6 +128,13 @@ struct GrayToRgb {
                                                uint32_t warp_u0, int nvalid, uint4 *stage, int lane)
     {
         using D = RgbPos<DL>;
+        if (FROM_Y8 && D::bpp == 4) {       // destination is read-modify-written: ask L2 for it now
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = j * 32 + lane;
+                if (c < nvalid * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d0 + doff + (size_t)warp_u0 * 64 + (size_t)c * 16));
+            }
+        }
         uint4 v = make_uint4(0, 0, 0, 0);
         if (valid) v = ldg128(p.s0 + soff + (size_t)u * 16);
         uint32_t gw[4] = {v.x, v.y, v.z, v.w};

@@ -470,7 +470,7 @@ bool launch_wordperm(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpi
 {
     const uint32_t nchunks = (uint32_t)(bytes / 16);
     if (nchunks == 0) return true;
-    long gx = ((long)sm_count() * 16 + nframes - 1) / nframes;
+    long gx = ((long)sm_count() * 8 * fast::waves(32) + nframes - 1) / nframes;
     const long maxgx = (nchunks + 255) / 256;
     if (gx < 1) gx = 1;
     if (gx > maxgx) gx = maxgx;
