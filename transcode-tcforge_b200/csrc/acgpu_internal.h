@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "acgpu.h"
 
 namespace acgpu {
@@ -51,9 +53,25 @@ bool convert_fast(const ConvertArgs &a);
 bool convert_tma(const ConvertArgs &a);
 
 // Row blends (rowops.cu).
-bool rowops_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
-                   const acgpu_rowop *d_ops, int nops, int row_bytes, int nframes, cudaStream_t st,
-                   bool offsets_aligned16);
+// One block of consecutive row operations with the distinct source rows it reads (host-built, see rowops.cu).
+struct RowTask {
+    int64_t  dest_off;
+    uint32_t w1, w2;
+    uint8_t  op, s1, s2, s3;      // ACGPU_ROW_* and slots into RowBlk::src_off
+    uint32_t pad;
+};
+struct RowBlk {
+    static constexpr int kRows = 8, kMaxSrc = 3 * kRows;
+    int32_t nsrc, nops;
+    int64_t src_off[kMaxSrc];
+    RowTask t[kRows];
+};
+int  build_row_blocks(const acgpu_rowop *ops, int nops, std::vector<RowBlk> &out);   // returns max distinct rows per block
+bool rowops_tiled_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const RowBlk *d_blks, int nblks,
+                         int max_nsrc, int row_bytes, int nframes, cudaStream_t st);
+bool rowops_bytes_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
+                         const acgpu_rowop *d_ops, int nops, int row_bytes, int nframes, cudaStream_t st);
+bool rowops_vectorisable(const uint8_t *src, size_t spitch, const uint8_t *dst, size_t dpitch, int row_bytes);
 bool blend_launch(const uint8_t *s1, const uint8_t *s2, uint8_t *d, size_t bytes,
                   uint32_t w1, uint32_t w2, int op, cudaStream_t st);
 bool resize_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,

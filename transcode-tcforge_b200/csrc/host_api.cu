@@ -706,11 +706,25 @@ int acgpu_rowops_run(const uint8_t *src, size_t spitch, uint8_t *dest, size_t dp
         if (two) al = al && (o.src2_off & 15) == 0;
         if (o.op == ACGPU_ROW_AVERAGE3) al = al && (o.src3_off & 15) == 0;
     }
+    const bool vec = al && rowops_vectorisable(src, spitch, dest, dpitch, row_bytes);
+    if (vec) {
+        std::vector<RowBlk> blks;
+        const int max_nsrc = build_row_blocks(ops, nops, blks);
+        const RowBlk *d_blks = static_cast<const RowBlk *>(device_blob(c, blks.data(), sizeof(RowBlk) * blks.size(), st));
+        if (!d_blks) return 0;
+        for (int f0 = 0; f0 < nframes; f0 += 32768) {
+            const int n = nframes - f0 < 32768 ? nframes - f0 : 32768;
+            if (!rowops_tiled_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, d_blks,
+                                     (int)blks.size(), max_nsrc, row_bytes, n, st))
+                return 0;
+        }
+        return 1;
+    }
     const acgpu_rowop *d_ops = static_cast<const acgpu_rowop *>(device_blob(c, ops, sizeof(acgpu_rowop) * (size_t)nops, st));
     if (!d_ops) return 0;
     for (int f0 = 0; f0 < nframes; f0 += 32768) {
         const int n = nframes - f0 < 32768 ? nframes - f0 : 32768;
-        if (!rowops_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, d_ops, nops, row_bytes, n, st, al))
+        if (!rowops_bytes_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, d_ops, nops, row_bytes, n, st))
             return 0;
     }
     return 1;

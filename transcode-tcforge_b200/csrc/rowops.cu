@@ -11,6 +11,10 @@
 #include "acgpu_internal.h"
 #include "pixmath.cuh"
 
+#include <string.h>
+
+#include <vector>
+
 namespace acgpu {
 namespace {
 
@@ -22,19 +26,24 @@ __device__ __forceinline__ uint32_t avg4x8(uint32_t a, uint32_t b)
     return (a | b) - (((a ^ b) >> 1) & 0x7F7F7F7Fu);
 }
 
+// Four bytes of (a*w1 + b*w2 + 32768) >> 16, low byte kept (aclib/rescale.c:44-45).  Both weights are < 65536 on
+// this path, so one dp2a (16-bit weights x 8-bit samples, SASS IDP.2A) forms a whole sum; PRMT pairs the samples
+// and picks byte 2 of each accumulator: 2.25 instructions per output byte.
 __device__ __forceinline__ uint32_t rescale4x8(uint32_t a, uint32_t b, uint32_t w1, uint32_t w2)
 {
-    uint32_t r = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t x = (a >> (8 * k)) & 0xFF, y = (b >> (8 * k)) & 0xFF;
-        r |= (((x * w1 + y * w2 + 32768u) >> 16) & 0xFFu) << (8 * k);
-    }
-    return r;
+    const uint32_t w = (w1 & 0xFFFFu) | (w2 << 16);
+    const uint32_t p01 = __byte_perm(a, b, 0x5140);   // a0 b0 a1 b1
+    const uint32_t p23 = __byte_perm(a, b, 0x7362);   // a2 b2 a3 b3
+    uint32_t r0, r1, r2, r3;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r0) : "r"(w), "r"(p01), "r"(32768u));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r1) : "r"(w), "r"(p01), "r"(32768u));
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r2) : "r"(w), "r"(p23), "r"(32768u));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r3) : "r"(w), "r"(p23), "r"(32768u));
+    return __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
 }
 
 __device__ __forceinline__ uint4 ld16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ void st16(uint8_t *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
+__device__ __forceinline__ void st16(uint8_t *p, uint4 v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
 
 __device__ __forceinline__ uint4 blend16(const acgpu_rowop &op, const uint8_t *s, size_t c)
 {
@@ -68,17 +77,62 @@ __device__ __forceinline__ uint8_t blend1(const acgpu_rowop &op, const uint8_t *
     return (uint8_t)rescale1(s[op.src1_off + c], s[op.src2_off + c], op.weight1, op.weight2);
 }
 
-// One thread per 16-byte chunk; chunks_per_row = row_bytes/16.
-__global__ void k_rowops_v16(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
-                             const acgpu_rowop *__restrict__ ops, int nops, int chunks_per_row)
+// Tiled row blends.  The host cuts the operation list into blocks of kRows consecutive operations and lists the
+// DISTINCT source rows each block reads (libtcvideo's shapes reuse rows between neighbouring outputs: deinterlace
+// reads y-1, y, y+1; resize reads overlapping two-tap windows).  A thread owns one 16-byte column of the tile:
+// it fires one 16-byte cp.async (LDGSTS, L2-only) per distinct source row -- all of them in flight at once, no
+// registers held -- waits, then computes the block's output rows from shared memory and streams them out.
+// Every source byte crosses L2->SM once per block instead of once per use, and per-thread memory parallelism is
+// the number of distinct rows (10 for deinterlace), which is what the one-chunk-per-thread version lacked
+// (ncu, profiles/r1c: 28 % issue, 24 cycles of long-scoreboard stall per instruction).
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
-    const size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
-    if (idx >= (size_t)nops * chunks_per_row) return;
-    const int row = (int)(idx / chunks_per_row);
-    const size_t c = (idx - (size_t)row * chunks_per_row) * 16;
-    const acgpu_rowop op = ops[row];
-    const uint8_t *s = src + (size_t)blockIdx.y * spitch;
-    st16(dst + (size_t)blockIdx.y * dpitch + op.dest_off + c, blend16(op, s, c));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ uint4 blend_words(int op, uint4 a, uint4 b, uint4 e, uint32_t w1, uint32_t w2)
+{
+    if (op == ACGPU_ROW_COPY) return a;
+    if (op == ACGPU_ROW_RESCALE)
+        return make_uint4(rescale4x8(a.x, b.x, w1, w2), rescale4x8(a.y, b.y, w1, w2), rescale4x8(a.z, b.z, w1, w2),
+                          rescale4x8(a.w, b.w, w1, w2));
+    uint4 r = make_uint4(avg4x8(a.x, b.x), avg4x8(a.y, b.y), avg4x8(a.z, b.z), avg4x8(a.w, b.w));
+    if (op == ACGPU_ROW_AVERAGE3) r = make_uint4(avg4x8(e.x, r.x), avg4x8(e.y, r.y), avg4x8(e.z, r.z), avg4x8(e.w, r.w));
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_rowops_tiled(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
+                                                     const RowBlk *__restrict__ blks, int row_bytes, int tile_bytes, int ntiles)
+{
+    extern __shared__ uint4 s_tile[];          // [nsrc][tile_chunks]
+    __shared__ RowBlk s_blk;
+    const int bi = blockIdx.x / ntiles, tile = blockIdx.x - bi * ntiles;
+    {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(blks + bi);
+        uint32_t *l = reinterpret_cast<uint32_t *>(&s_blk);
+        for (int i = threadIdx.x; i < (int)(sizeof(RowBlk) / 4); i += blockDim.x) l[i] = g[i];
+    }
+    __syncthreads();
+    const int tchunks = tile_bytes >> 4, c = threadIdx.x;
+    const size_t col = (size_t)tile * tile_bytes + (size_t)c * 16;
+    if (c >= tchunks || col >= (size_t)row_bytes) return;
+    const uint8_t *s = src + (size_t)blockIdx.y * spitch + col;
+    uint8_t *d = dst + (size_t)blockIdx.y * dpitch + col;
+    const int nsrc = s_blk.nsrc;
+    for (int r = 0; r < nsrc; r++) cp_async16(&s_tile[r * tchunks + c], s + s_blk.src_off[r]);
+    cp_async_wait_all();
+    const int nops = s_blk.nops;
+    for (int k = 0; k < nops; k++) {
+        const RowTask t = s_blk.t[k];
+        const uint4 a = s_tile[t.s1 * tchunks + c];
+        const uint4 b = s_tile[t.s2 * tchunks + c];
+        const uint4 e = s_tile[t.s3 * tchunks + c];
+        st16(d + t.dest_off, blend_words(t.op, a, b, e, t.w1, t.w2));
+    }
 }
 
 __global__ void k_rowops_bytes(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
@@ -138,26 +192,76 @@ inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
 
-bool rowops_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
-                   const acgpu_rowop *d_ops, int nops, int row_bytes, int nframes, cudaStream_t st,
-                   bool offsets_aligned16)
+// Host side of the tiled kernel: blocks of kRows operations with their distinct source rows.
+int build_row_blocks(const acgpu_rowop *ops, int nops, std::vector<RowBlk> &out)
+{
+    int max_nsrc = 1;
+    out.clear();
+    for (int i0 = 0; i0 < nops; i0 += RowBlk::kRows) {
+        RowBlk b;
+        memset(&b, 0, sizeof(b));
+        b.nops = nops - i0 < RowBlk::kRows ? nops - i0 : RowBlk::kRows;
+        auto slot = [&](int64_t off) -> uint8_t {
+            for (int r = 0; r < b.nsrc; r++)
+                if (b.src_off[r] == off) return (uint8_t)r;
+            b.src_off[b.nsrc] = off;
+            return (uint8_t)b.nsrc++;
+        };
+        for (int k = 0; k < b.nops; k++) {
+            const acgpu_rowop &o = ops[i0 + k];
+            RowTask &t = b.t[k];
+            t.dest_off = o.dest_off;
+            t.w1 = o.weight1; t.w2 = o.weight2;
+            // aclib/rescale.c:26-29: a weight >= 65536 turns the blend into a copy and the other row is NEVER read
+            if (o.op == ACGPU_ROW_COPY || (o.op == ACGPU_ROW_RESCALE && o.weight1 >= 0x10000u)) {
+                t.op = ACGPU_ROW_COPY; t.s1 = t.s2 = t.s3 = slot(o.src1_off);
+            } else if (o.op == ACGPU_ROW_RESCALE && o.weight2 >= 0x10000u) {
+                t.op = ACGPU_ROW_COPY; t.s1 = t.s2 = t.s3 = slot(o.src2_off);
+            } else {
+                t.op = (uint8_t)o.op;
+                t.s1 = slot(o.src1_off);
+                t.s2 = slot(o.src2_off);
+                t.s3 = o.op == ACGPU_ROW_AVERAGE3 ? slot(o.src3_off) : t.s1;
+            }
+        }
+        if (b.nsrc > max_nsrc) max_nsrc = b.nsrc;
+        out.push_back(b);
+    }
+    return max_nsrc;
+}
+
+bool rowops_tiled_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const RowBlk *d_blks, int nblks,
+                         int max_nsrc, int row_bytes, int nframes, cudaStream_t st)
+{
+    if (nblks <= 0 || row_bytes <= 0 || nframes <= 0) return true;
+    const int ntiles = (row_bytes + 2047) / 2048;
+    const int tile_bytes = (((row_bytes + ntiles - 1) / ntiles) + 15) / 16 * 16;
+    const int threads = ((tile_bytes / 16) + 31) / 32 * 32;
+    const size_t smem = (size_t)max_nsrc * tile_bytes;
+    if (smem > 48 * 1024 && !check(cudaFuncSetAttribute(k_rowops_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
+        return false;
+    dim3 g((unsigned)(nblks * ntiles), (unsigned)nframes);
+    k_rowops_tiled<<<g, threads, smem, st>>>(src, spitch, dst, dpitch, d_blks, row_bytes, tile_bytes, ntiles);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_rowops_tiled");
+    return true;
+}
+
+bool rowops_bytes_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
+                         const acgpu_rowop *d_ops, int nops, int row_bytes, int nframes, cudaStream_t st)
 {
     if (nops <= 0 || row_bytes <= 0 || nframes <= 0) return true;
-    const bool vec = offsets_aligned16 && aligned16(src) && aligned16(dst) && spitch % 16 == 0 && dpitch % 16 == 0
-                  && row_bytes % 16 == 0;
-    if (vec) {
-        const int cpr = row_bytes / 16;
-        const size_t n = (size_t)nops * cpr;
-        dim3 g((unsigned)((n + TPB - 1) / TPB), (unsigned)nframes);
-        k_rowops_v16<<<g, TPB, 0, st>>>(src, spitch, dst, dpitch, d_ops, nops, cpr);
-    } else {
-        const size_t n = (size_t)nops * row_bytes;
-        dim3 g((unsigned)((n + TPB - 1) / TPB), (unsigned)nframes);
-        k_rowops_bytes<<<g, TPB, 0, st>>>(src, spitch, dst, dpitch, d_ops, nops, row_bytes);
-    }
+    const size_t n = (size_t)nops * row_bytes;
+    dim3 g((unsigned)((n + TPB - 1) / TPB), (unsigned)nframes);
+    k_rowops_bytes<<<g, TPB, 0, st>>>(src, spitch, dst, dpitch, d_ops, nops, row_bytes);
     note_launch();
-    ACGPU_CHECK_LAUNCH("k_rowops");
+    ACGPU_CHECK_LAUNCH("k_rowops_bytes");
     return true;
+}
+
+bool rowops_vectorisable(const uint8_t *src, size_t spitch, const uint8_t *dst, size_t dpitch, int row_bytes)
+{
+    return aligned16(src) && aligned16(dst) && spitch % 16 == 0 && dpitch % 16 == 0 && row_bytes % 16 == 0;
 }
 
 bool blend_launch(const uint8_t *s1, const uint8_t *s2, uint8_t *d, size_t bytes,
