@@ -656,8 +656,9 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
     const size_t sfb = frame_bytes(sf, width, height), dfb = frame_bytes(df, width, height);
     const size_t sp = align_up(sfb, 256), dp = align_up(dfb, 256);     // device frame pitches
     const bool preload = !overwrites_whole_dest(sf, df, width, height);
-    // ~32 MiB of the larger side per chunk: big enough to amortise launches, small enough to pipeline
-    size_t per = (size_t)(32u << 20) / (sp > dp ? sp : dp);
+    // ~16 MiB of the larger side per chunk: big enough to amortise launches and reach full PCIe rate (tools/pcie_probe.py:
+    // 16 MB copies already run at 56 GB/s), small enough that the fill/drain bubbles of the pipeline stay short
+    size_t per = (size_t)(16u << 20) / (sp > dp ? sp : dp);
     if (per < 1) per = 1;
     if (per > (size_t)nframes) per = nframes;
     const size_t slot_bytes = per * (sp + dp);
