@@ -49,7 +49,7 @@ bool convert_generic(const ConvertArgs &a);
 // Tier 2: 16-byte vectorised kernels; returns false (without launching) when the pair/size/alignment
 // is outside its domain so the caller can fall back to tier 1 (kernels_fast.cu).
 bool convert_fast(const ConvertArgs &a);
-// Tier 3: TMA/bulk-copy staged persistent kernels for the headline pairs (kernels_tma.cu).
+// Tier 3: the tier-2 YUV->RGB24 kernels with bulk (TMA) stores of the output tile (kernels_fast.cu); selectable only.
 bool convert_tma(const ConvertArgs &a);
 
 // Row blends (rowops.cu).
