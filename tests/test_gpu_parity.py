@@ -248,3 +248,27 @@ def test_odd_heights_and_widths_where_the_c_path_is_well_defined(ac, chk):
         _, want = chk.convert(src, sf, df, w, h)
         assert ok == 1
         assert_same(got, want, f"{F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h}")
+
+
+def test_device_guard_bands_all_pairs(ac, chk):
+    """Kernels must not write outside [dest, dest + frame_bytes): canaries before and after every device frame.
+    (compute-sanitizer is closed on this GPU pool, so overruns are caught this way.)"""
+    w, h, nf, guard = 128, 8, 2, 512
+    for srcfmt, dstfmt in ALL_PAIRS:
+        sfb, dfb = F.frame_bytes(srcfmt, w, h), F.frame_bytes(dstfmt, w, h)
+        dpitch = dfb + guard
+        frames = np.stack([ck.random_frame(srcfmt, w, h, seed=70 + i) for i in range(nf)])
+        ds = ac.malloc(nf * sfb).upload(frames.reshape(-1))
+        dd = ac.malloc(guard + nf * dpitch).fill(0xC3)
+        for tier in (0, 1):
+            ac.lib.acgpu_force_tier(tier)
+            try:
+                ac._ok(ac.imgconvert_batch(ds.ptr, srcfmt, sfb, dd.ptr + guard, dstfmt, dpitch, w, h, nf))
+            finally:
+                ac.lib.acgpu_force_tier(0)
+            ac.sync()
+            out = dd.download()
+            assert (out[:guard] == 0xC3).all(), f"underrun {F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} tier {tier}"
+            body = out[guard:].reshape(nf, dpitch)
+            assert (body[:, dfb:] == 0xC3).all(), f"overrun {F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} tier {tier}"
+        ds.free(); dd.free()
