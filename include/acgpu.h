@@ -128,6 +128,15 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
                        int resize_w, int resize_h, int scale_w, int scale_h,
                        size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
 
+/* tcv_convert (libtcvideo/tcvideo.c:1001-1067) on device-resident frames: planes are laid out as YUV_INIT_PLANES
+ * does, equal formats copy, and src == dest converts through an internal temporary exactly like the reference. */
+int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, ImageFormat srcfmt, ImageFormat destfmt,
+                        size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+/* transcode's -K on RGB24 frames (src/video_trans.c:381-388: RGB24 -> GRAY8 -> RGB24) fused into one in-place pass;
+ * byte-identical to the two ac_imgconvert calls, half the memory traffic. */
+int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t frame_pitch, int nframes,
+                              acgpu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

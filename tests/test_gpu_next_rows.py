@@ -1,0 +1,81 @@
+"""-m gpu parity for the "next" rows of SURVEY.md 8f that are built: device-resident tcv_convert
+(libtcvideo/tcvideo.c:1001-1067) and the fused -K grayscale of src/video_trans.c:381-388."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+import checkers as ck
+from checkers import F
+
+pkg = entry.load_package()
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ac():
+    a = pkg.AcGpu()
+    assert a.ac_init(pkg.AC_ALL) == 1, a.last_error()
+    return a
+
+
+@pytest.fixture(scope="module")
+def chk():
+    return ck.best_checker()
+
+
+@pytest.mark.parametrize("size", [(1920, 1080), (128, 16), (50, 7), (766, 512)])
+def test_decolor_rgb24_equals_the_two_reference_conversions(ac, chk, size):
+    w, h = size
+    nf = 2
+    fb = w * h * 3
+    frames = np.stack([ck.splitmix_bytes(fb, 90 + i) for i in range(nf)])
+    want = []
+    for i in range(nf):
+        _, g = chk.convert(frames[i], F.IMG_RGB24, F.IMG_GRAY8, w, h, pad=0)
+        _, r = chk.convert(g, F.IMG_GRAY8, F.IMG_RGB24, w, h, pad=0)
+        want.append(r)
+    pitch = fb + 256 - fb % 256 if fb % 256 else fb + 256
+    buf = ac.malloc(nf * pitch).fill(0x55)
+    for i in range(nf):
+        buf.upload(frames[i], offset=i * pitch)
+    ac._ok(ac.lib.acgpu_decolor_rgb24_batch(buf.ptr, w, h, pitch, nf, None))
+    ac.sync()
+    out = buf.download().reshape(nf, pitch)
+    for i in range(nf):
+        assert np.array_equal(out[i, :fb], want[i]), (size, i)
+    assert (out[:, fb:] == 0x55).all()
+    buf.free()
+
+
+def test_convert_batch_matches_tcv_convert_semantics(ac, chk):
+    w, h, nf = 128, 16, 3
+    # different buffers
+    for sf, df in [(F.IMG_YUV420P, F.IMG_RGB24), (F.IMG_YV12, F.IMG_BGRA32), (F.IMG_RGB24, F.IMG_YUV422P), (F.IMG_UYVY, F.IMG_YUV420P)]:
+        sfb, dfb = F.frame_bytes(sf, w, h), F.frame_bytes(df, w, h)
+        frames = np.stack([ck.random_frame(sf, w, h, seed=30 + i) for i in range(nf)])
+        ds = ac.malloc(nf * sfb).upload(frames.reshape(-1))
+        dd = ac.malloc(nf * dfb).fill(0x55)
+        ac._ok(ac.lib.acgpu_convert_batch(ds.ptr, dd.ptr, w, h, sf, df, sfb, dfb, nf, None))
+        ac.sync()
+        got = dd.download().reshape(nf, dfb)
+        for i in range(nf):
+            assert np.array_equal(got[i], chk.convert(frames[i], sf, df, w, h, pad=0)[1]), (sf, df, i)
+        ds.free(); dd.free()
+    # in place (src == dest): converted through a temporary like tcvideo.c:1044-1064
+    sf, df = F.IMG_RGB24, F.IMG_YUV420P
+    sfb, dfb = F.frame_bytes(sf, w, h), F.frame_bytes(df, w, h)
+    frames = np.stack([ck.random_frame(sf, w, h, seed=40 + i) for i in range(nf)])
+    buf = ac.malloc(nf * sfb).upload(frames.reshape(-1))
+    ac._ok(ac.lib.acgpu_convert_batch(buf.ptr, buf.ptr, w, h, sf, df, sfb, sfb, nf, None))
+    ac.sync()
+    got = buf.download().reshape(nf, sfb)
+    for i in range(nf):
+        assert np.array_equal(got[i, :dfb], chk.convert(frames[i], sf, df, w, h, pad=0)[1])
+        assert np.array_equal(got[i, dfb:], frames[i, dfb:])         # bytes beyond the new frame are untouched
+    # same format: plain copy
+    dd = ac.malloc(nf * sfb).fill(0)
+    ac._ok(ac.lib.acgpu_convert_batch(buf.ptr, dd.ptr, w, h, sf, sf, sfb, sfb, nf, None))
+    ac.sync()
+    assert np.array_equal(dd.download(), buf.download())
+    assert ac.lib.acgpu_convert_batch(buf.ptr, dd.ptr, w, h, 0, sf, sfb, sfb, nf, None) == 0
+    buf.free(); dd.free()

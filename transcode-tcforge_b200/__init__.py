@@ -53,6 +53,7 @@ ABI_SYMBOLS = [
     "acgpu_stream_sync", "acgpu_event_create", "acgpu_event_destroy", "acgpu_event_record",
     "acgpu_event_sync", "acgpu_event_elapsed_ms", "acgpu_imgconvert_batch", "acgpu_imgconvert_frames_host",
     "acgpu_rowops_run", "acgpu_average", "acgpu_rescale", "acgpu_deinterlace_batch", "acgpu_resize_batch",
+    "acgpu_convert_batch", "acgpu_decolor_rgb24_batch",
 ]
 
 
@@ -86,6 +87,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "acgpu_average": (i32, [vp, vp, vp, sz, vp]), "acgpu_rescale": (i32, [vp, vp, vp, sz, u32, u32, vp]),
         "acgpu_deinterlace_batch": (i32, [vp, vp, i32, i32, i32, i32, sz, sz, i32, vp]),
         "acgpu_resize_batch": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, sz, sz, i32, vp]),
+        "acgpu_convert_batch": (i32, [vp, vp, i32, i32, i32, i32, sz, sz, i32, vp]),
+        "acgpu_decolor_rgb24_batch": (i32, [vp, i32, i32, sz, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

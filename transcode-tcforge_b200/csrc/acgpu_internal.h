@@ -52,6 +52,9 @@ bool convert_fast(const ConvertArgs &a);
 // Tier 3: the tier-2 YUV->RGB24 kernels with bulk (TMA) stores of the output tile (kernels_fast.cu); selectable only.
 bool convert_tma(const ConvertArgs &a);
 
+// Fused RGB24 -> gray -> RGB24 in place (kernels_fast_rgb.cu); false when outside the vectorised domain.
+bool decolor_rgb24_fast(uint8_t *frames, size_t pitch, int w, int h, int nframes, cudaStream_t st);
+
 // Row blends (rowops.cu).
 // One block of consecutive row operations with the distinct source rows it reads (host-built, see rowops.cu).
 struct RowTask {

@@ -882,4 +882,54 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     return 1;
 }
 
+int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, ImageFormat srcfmt, ImageFormat destfmt,
+                        size_t spitch, size_t dpitch, int nframes, acgpu_stream_t stream)
+{
+    // libtcvideo/tcvideo.c:1001-1067
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (!src || !dest || width <= 0 || height <= 0 || !srcfmt || !destfmt) { set_error("acgpu_convert_batch: invalid image parameters"); return 0; }
+    const int sf = srcfmt == IMG_YV12 ? IMG_YUV420P : (int)srcfmt, df = destfmt == IMG_YV12 ? IMG_YUV420P : (int)destfmt;
+    if (describe(sf).kind == K_NONE || describe(df).kind == K_NONE) { set_error("acgpu_convert_batch: unknown format"); return 0; }
+    if (nframes <= 0) return 1;
+    cudaStream_t st = pick_stream(c, stream);
+    const size_t sfb = frame_bytes(sf, width, height), dfb = frame_bytes(df, width, height);
+    if (srcfmt == destfmt) {
+        if (src == dest) return 1;
+        return check(cudaMemcpy2DAsync(dest, dpitch ? dpitch : dfb, src, spitch ? spitch : sfb, dfb, nframes,
+                                       cudaMemcpyDeviceToDevice, st), "acgpu_convert_batch copy") ? 1 : 0;
+    }
+    uint8_t *real = dest;
+    size_t rpitch = dpitch;
+    if (src == dest) {                    // in place: convert into a temporary, then copy back (tcvideo.c:1044-1064)
+        rpitch = align_up(dfb, 256);
+        if (!ensure_arena(c, rpitch * (size_t)nframes)) return 0;
+        real = c->arena;
+    }
+    uint8_t *sp[3], *dp[3];
+    sp[0] = src;  sp[1] = src + (size_t)width * height;  sp[2] = sp[1] + chroma_plane_bytes(sf, width, height);
+    dp[0] = real; dp[1] = real + (size_t)width * height; dp[2] = dp[1] + chroma_plane_bytes(df, width, height);
+    if (!acgpu_imgconvert_batch(sp, srcfmt, spitch, dp, destfmt, rpitch, width, height, nframes, stream)) return 0;
+    if (src == dest)
+        return check(cudaMemcpy2DAsync(dest, dpitch ? dpitch : dfb, real, rpitch, dfb, nframes, cudaMemcpyDeviceToDevice, st),
+                     "acgpu_convert_batch copy back") ? 1 : 0;
+    return 1;
+}
+
+int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t pitch, int nframes, acgpu_stream_t stream)
+{
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (!frames || width <= 0 || height <= 0) { set_error("acgpu_decolor_rgb24_batch: invalid frame parameters"); return 0; }
+    if (nframes <= 0) return 1;
+    cudaStream_t st = pick_stream(c, stream);
+    if (tls.force_tier != 1 && decolor_rgb24_fast(frames, pitch, width, height, nframes, st)) { tls.last_tier = 2; return 1; }
+    // outside the vectorised domain: the reference's own two steps through a temporary gray plane
+    const size_t gpitch = align_up((size_t)width * height, 256);
+    if (!ensure_arena(c, gpitch * (size_t)nframes)) return 0;
+    uint8_t *rgb[3] = {frames, nullptr, nullptr}, *gray[3] = {c->arena, nullptr, nullptr};
+    return acgpu_imgconvert_batch(rgb, IMG_RGB24, pitch, gray, IMG_GRAY8, gpitch, width, height, nframes, stream)
+        && acgpu_imgconvert_batch(gray, IMG_GRAY8, gpitch, rgb, IMG_RGB24, pitch, width, height, nframes, stream);
+}
+
 }  // extern "C"

@@ -171,6 +171,47 @@ struct GrayToRgb {
     }
 };
 
+// -K on RGB24 (src/video_trans.c:381-388): gray = (19595 R + 38470 G + 7471 B + 32768) >> 16 written to all three
+// channels.  One pass, in place: a warp reads its own 1536-byte tile completely before it writes it back.
+struct DecolorRgb24 {
+    static constexpr int kStage = 3;
+    static __device__ __forceinline__ void run(const FastParams &p, size_t soff, size_t doff, uint32_t u, bool valid,
+                                               uint32_t warp_u0, int nvalid, uint4 *stage, int lane)
+    {
+        using RI = RgbInfo<L_RGB24>;
+        constexpr uint32_t lo = RI::half(19595, 38470, 7471, 0), hi = RI::half(19595, 38470, 7471, 2);
+        uint32_t px[16], ow[12];
+        {
+            uint32_t w[12];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {     // plain loads: the source is also the destination
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (valid) v = *reinterpret_cast<const uint4 *>(p.s0 + soff + (size_t)u * 48 + k * 16);
+                w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                px[4 * g + 0] = w[3 * g];
+                px[4 * g + 1] = __byte_perm(w[3 * g], w[3 * g + 1], 0x0543);
+                px[4 * g + 2] = __byte_perm(w[3 * g + 1], w[3 * g + 2], 0x0432);
+                px[4 * g + 3] = w[3 * g + 2] >> 8;
+            }
+        }
+        __syncwarp();      // every lane has its pixels before any lane's tile bytes are overwritten
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t a[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) a[k] = dp2a_hi_uu(hi, px[4 * g + k], dp2a_lo_uu(lo, px[4 * g + k], 32768u));
+            const uint32_t gw = pack_b2x4(a[0], a[1], a[2], a[3]);
+            ow[3 * g + 0] = __byte_perm(gw, 0, 0x1000);
+            ow[3 * g + 1] = __byte_perm(gw, 0, 0x2211);
+            ow[3 * g + 2] = __byte_perm(gw, 0, 0x3332);
+        }
+        store_chunks<3>(stage, lane, ow, p.d0 + doff + (size_t)warp_u0 * 48, nvalid);
+    }
+};
+
 int layout_of(int fmt)
 {
     switch (fmt) {
@@ -227,6 +268,16 @@ bool dispatch_gray_dst(int dl, const FastParams &p, int nf, cudaStream_t st)
 }
 
 }  // namespace
+
+bool decolor_rgb24_fast(uint8_t *frames, size_t pitch, int w, int h, int nframes, cudaStream_t st)
+{
+    const size_t P = (size_t)w * h;
+    if (!al16(frames) || (nframes > 1 && pitch % 16) || P % 16 || P / 16 > 0x7FFFFFFFu) return false;
+    FastParams p{};
+    p.s0 = frames; p.d0 = frames; p.spitch = p.dpitch = pitch;
+    p.w = w; p.h = h; p.nunits = (uint32_t)(P / 16);
+    return launch_rgb<DecolorRgb24>(p, nframes, st, "decolor_rgb24");
+}
 
 bool fast_rgb_family(const ConvertArgs &a, const fast::FastParams &p)
 {
