@@ -865,9 +865,37 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     if (resize_w) {
         build_resize_table(width * 8 / scale_w, new_w * 8 / scale_w, ts, w1, w2);
         const int n = (int)ts.size();
+        const size_t sp_ = spitch ? spitch : (size_t)width * height * Bpp, dp_ = dpitch ? dpitch : (size_t)new_w * new_h * Bpp;
+        if (resize_h_vectorisable(src, sp_, dest, dp_, width, new_w, Bpp)) {
+            // per-row byte tables: source byte offset (first tap) and packed weights for every output byte of a row
+            const int src_block = width / scale_w, dst_block = new_w / scale_w;
+            std::vector<uint16_t> off((size_t)new_w * Bpp);
+            std::vector<uint32_t> wgt((size_t)new_w * Bpp);
+            for (int b = 0; b < scale_w; b++)
+                for (int x = 0; x < dst_block; x++)
+                    for (int k = 0; k < Bpp; k++) {
+                        const size_t o = ((size_t)b * dst_block + x) * Bpp + k;
+                        size_t so = ((size_t)b * src_block + ts[x]) * Bpp + k;
+                        uint32_t wp;
+                        if (w1[x] >= 0x10000u) wp = 0x0000FFFFu;                          // tap 1 untouched
+                        else if (w2[x] >= 0x10000u) { wp = 0x0000FFFFu; so += Bpp; }      // w1 == 0: tap 2 untouched
+                        else wp = (w1[x] & 0xFFFFu) | (w2[x] << 16);
+                        off[o] = (uint16_t)so;
+                        wgt[o] = wp;
+                    }
+            const uint16_t *doff = static_cast<const uint16_t *>(device_blob(c, off.data(), off.size() * sizeof(uint16_t), st));
+            const uint32_t *dwgt = static_cast<const uint32_t *>(device_blob(c, wgt.data(), wgt.size() * sizeof(uint32_t), st));
+            if (!doff || !dwgt) return 0;
+            for (int f0 = 0; f0 < nframes; f0 += 32768) {
+                const int nf = nframes - f0 < 32768 ? nframes - f0 : 32768;
+                if (!resize_h_row_launch(src + (size_t)f0 * sp_, sp_, dest + (size_t)f0 * dp_, dp_, doff, dwgt, width, new_w,
+                                         new_h, Bpp, nf, st))
+                    return 0;
+            }
+            return 1;
+        }
         const int32_t *dts = static_cast<const int32_t *>(device_blob(c, ts.data(), sizeof(int32_t) * n, st));
         const uint32_t *dw1 = static_cast<const uint32_t *>(device_blob(c, w1.data(), sizeof(uint32_t) * n, st));
-        // w2 may hash-collide with w1 only if equal in content, which is then the same table anyway
         const uint32_t *dw2 = static_cast<const uint32_t *>(device_blob(c, w2.data(), sizeof(uint32_t) * n, st));
         if (!dts || !dw1 || !dw2) return 0;
         for (int f0 = 0; f0 < nframes; f0 += 32768) {
