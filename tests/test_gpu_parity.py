@@ -272,3 +272,38 @@ def test_device_guard_bands_all_pairs(ac, chk):
             body = out[guard:].reshape(nf, dpitch)
             assert (body[:, dfb:] == 0xC3).all(), f"overrun {F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} tier {tier}"
         ds.free(); dd.free()
+
+
+def test_concurrent_callers_like_transcode_frame_threads(ac, chk):
+    """src/frame_threads.c:174-228: N frame threads hit ac_imgconvert / ac_average concurrently and re-entrantly.
+    Every thread gets its own stream and staging buffers inside libacgpu; results must not mix."""
+    import threading
+    w, h, rounds = 320, 240, 6
+    pairs = [(F.IMG_YUV420P, F.IMG_RGB24), (F.IMG_RGB24, F.IMG_YUV420P), (F.IMG_YUY2, F.IMG_YUV422P), (F.IMG_YUV422P, F.IMG_BGRA32),
+             (F.IMG_UYVY, F.IMG_RGB24), (F.IMG_RGBA32, F.IMG_YUY2), (F.IMG_YUV444P, F.IMG_YUV420P), (F.IMG_GRAY8, F.IMG_RGB24)]
+    want = {}
+    for t, (sf, df) in enumerate(pairs):
+        for r in range(rounds):
+            src = ck.random_frame(sf, w, h, seed=1000 + 10 * t + r)
+            want[(t, r)] = (src, chk.convert(src, sf, df, w, h)[1])
+    errors = []
+
+    def worker(t):
+        sf, df = pairs[t]
+        mine = pkg.AcGpu()          # same library, this thread's own thread-local context
+        try:
+            for r in range(rounds):
+                src, exp = want[(t, r)]
+                ok, got = mine.convert(src, sf, df, w, h)
+                if ok != 1 or not np.array_equal(got, exp):
+                    errors.append((t, r, "convert"))
+                a, b = src[:4096].copy(), src[4096:8192].copy()
+                if not np.array_equal(mine.ac_average(a, b), ((a.astype(np.int32) + b + 1) // 2).astype(np.uint8)):
+                    errors.append((t, r, "average"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(len(pairs))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
