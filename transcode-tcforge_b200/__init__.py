@@ -18,7 +18,7 @@ from . import formats as F
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-LIB_PATH = os.path.join(_HERE, "libacgpu.so")
+LIB_PATH = os.environ.get("ACGPU_LIB") or os.path.join(_HERE, "libacgpu.so")   # ACGPU_LIB: A/B builds while profiling
 
 AC_NONE = 0
 AC_ALL = -1
