@@ -201,25 +201,21 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
         const bool valid = unit < p.upr;
         const int nvalid = min(32, p.upr - warp * 32);
         if (nvalid <= 0) return;
-        // running pointers: one 64-bit add per plane per trip instead of re-deriving every address from (rp, unit)
-        const uint8_t *yp = Y + (size_t)(2 * blockIdx.x) * p.w + unit * 16;
-        const uint8_t *up = U + (size_t)blockIdx.x * (p.w >> 1) + unit * 8;
-        const uint8_t *vp = V + (size_t)blockIdx.x * (p.w >> 1) + unit * 8;
-        uint8_t *row0 = dst + ((size_t)(2 * blockIdx.x) * p.w + warp * 512) * BPP;
-        const size_t ystep = (size_t)gridDim.x * 2 * p.w, cstep = (size_t)gridDim.x * (p.w >> 1);
-        const size_t dstep = ystep * BPP, rowb = (size_t)p.w * BPP;
-        for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x, yp += ystep, up += cstep, vp += cstep, row0 += dstep) {
+        for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
             uint32_t y0[4] = {0, 0, 0, 0}, y1[4] = {0, 0, 0, 0};
             uint2 uu = make_uint2(0, 0), vv = make_uint2(0, 0);
             if (valid) {
+                const uint8_t *yp = Y + (size_t)(2 * rp) * p.w + unit * 16;
                 const uint4 a = ldg128(yp), b = ldg128(yp + p.w);
                 y0[0] = a.x; y0[1] = a.y; y0[2] = a.z; y0[3] = a.w;
                 y1[0] = b.x; y1[1] = b.y; y1[2] = b.z; y1[3] = b.w;
-                uu = ldg64(up);
-                vv = ldg64(vp);
+                const size_t co = (size_t)rp * (p.w >> 1) + unit * 8;
+                uu = ldg64(U + co);
+                vv = ldg64(V + co);
             }
+            uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + warp * 512) * BPP;
             prefetch_dest_row<BPP>(row0, lane, nvalid);
-            prefetch_dest_row<BPP>(row0 + rowb, lane, nvalid);
+            prefetch_dest_row<BPP>(row0 + (size_t)p.w * BPP, lane, nvalid);
             int cr[8], cg[8], cb[8];
 #pragma unroll
             for (int s = 0; s < 8; s++)
@@ -229,8 +225,8 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
             if (BULK) store_row_bulk<BPP>(stage, lane, ow, row0, nvalid);
             else store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0, nvalid);
             convert_row<SRC, SWAP, BPP, AFIRST>(y1, cr, cg, cb, ow);
-            if (BULK) store_row_bulk<BPP>(stage2, lane, ow, row0 + rowb, nvalid);
-            else store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0 + rowb, nvalid);
+            if (BULK) store_row_bulk<BPP>(stage2, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+            else store_row_rgb<BPP, AFIRST>(stage, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
         }
         if (BULK && lane == 0) bulk_wait_all<0>();
     } else {
