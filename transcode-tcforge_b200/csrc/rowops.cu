@@ -194,33 +194,39 @@ __global__ void k_resize_h(const uint8_t *src, size_t spitch, uint8_t *dst, size
 // the two taps are gathered from shared memory and blended with one dp2a.  A copy tap (weight1 >= 65536, the
 // source pixel must be returned untouched and the second tap must not be read: tcvideo.c:517-531) is encoded as
 // weights (65535, 0) with both taps on the same byte: (a*65535 + 32768) >> 16 == a for every byte a.
-__global__ void __launch_bounds__(128) k_resize_h_row(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
+constexpr int kResizeRows = 4;      // image rows per block: amortises the stage/sync and keeps 4 rows of loads in flight
+__global__ void __launch_bounds__(256) k_resize_h_row(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
                                                      const uint16_t *__restrict__ toff, const uint32_t *__restrict__ twgt,
                                                      int src_row_bytes, int dst_row_bytes, int Bpp, int rows)
 {
     extern __shared__ uint4 s_row[];
-    const int row = blockIdx.x;
-    if (row >= rows) return;
-    const uint8_t *s = src + (size_t)blockIdx.y * spitch + (size_t)row * src_row_bytes;
-    uint8_t *d = dst + (size_t)blockIdx.y * dpitch + (size_t)row * dst_row_bytes;
-    for (int c = threadIdx.x; c < (src_row_bytes >> 4); c += blockDim.x) cp_async16(&s_row[c], s + (size_t)c * 16);
+    const int row0 = blockIdx.x * kResizeRows;
+    const int nrows = min(kResizeRows, rows - row0);
+    const uint8_t *s = src + (size_t)blockIdx.y * spitch + (size_t)row0 * src_row_bytes;
+    uint8_t *d = dst + (size_t)blockIdx.y * dpitch + (size_t)row0 * dst_row_bytes;
+    const int schunks = (src_row_bytes >> 4) * nrows;          // the rows are contiguous in the frame
+    for (int c = threadIdx.x; c < schunks; c += blockDim.x) cp_async16(&s_row[c], s + (size_t)c * 16);
     cp_async_wait_all();
     __syncthreads();
     const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_row);
-    for (int ow = threadIdx.x; ow < (dst_row_bytes >> 2); ow += blockDim.x) {
+    const int wpr = dst_row_bytes >> 2;
+    for (int ow = threadIdx.x; ow < wpr; ow += blockDim.x) {
         const uint2 o2 = __ldg(reinterpret_cast<const uint2 *>(toff) + ow);      // four 16-bit offsets
         const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(twgt) + ow);      // four weight pairs
         const uint32_t off[4] = {o2.x & 0xFFFFu, o2.x >> 16, o2.y & 0xFFFFu, o2.y >> 16};
         const uint32_t wt[4] = {w4.x, w4.y, w4.z, w4.w};
-        uint32_t r[4];
+        for (int r = 0; r < nrows; r++) {
+            const uint8_t *rb = sb + (size_t)r * src_row_bytes;
+            uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t a = sb[off[j]];
-            const uint32_t b = sb[off[j] + ((wt[j] >> 16) ? Bpp : 0)];           // copy taps: never look at the neighbour
-            asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r[j]) : "r"(wt[j]), "r"(a | (b << 8)), "r"(32768u));
+            for (int j = 0; j < 4; j++) {
+                const uint32_t a = rb[off[j]];
+                const uint32_t b = rb[off[j] + ((wt[j] >> 16) ? Bpp : 0)];       // copy taps: never look at the neighbour
+                asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(v[j]) : "r"(wt[j]), "r"(a | (b << 8)), "r"(32768u));
+            }
+            __stcs(reinterpret_cast<uint32_t *>(d + (size_t)r * dst_row_bytes) + ow,
+                   __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410));
         }
-        __stcs(reinterpret_cast<uint32_t *>(d) + ow,
-               __byte_perm(__byte_perm(r[0], r[1], 0x0062), __byte_perm(r[2], r[3], 0x0062), 0x5410));
     }
 }
 
@@ -317,11 +323,11 @@ bool resize_h_row_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t
 {
     const int srb = width * Bpp, drb = new_w * Bpp;
     if (rows <= 0 || nframes <= 0) return true;
-    const size_t smem = (size_t)srb + 16;
+    const size_t smem = (size_t)srb * kResizeRows + 16;
     if (smem > 48 * 1024 && !check(cudaFuncSetAttribute(k_resize_h_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
         return false;
-    dim3 g((unsigned)rows, (unsigned)nframes);
-    k_resize_h_row<<<g, 128, smem, st>>>(src, spitch, dst, dpitch, d_off, d_wgt, srb, drb, Bpp, rows);
+    dim3 g((unsigned)((rows + kResizeRows - 1) / kResizeRows), (unsigned)nframes);
+    k_resize_h_row<<<g, 256, smem, st>>>(src, spitch, dst, dpitch, d_off, d_wgt, srb, drb, Bpp, rows);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_resize_h_row");
     return true;
@@ -330,7 +336,7 @@ bool resize_h_row_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t
 bool resize_h_vectorisable(const uint8_t *src, size_t spitch, const uint8_t *dst, size_t dpitch, int width, int new_w, int Bpp)
 {
     return aligned16(src) && aligned16(dst) && spitch % 16 == 0 && dpitch % 16 == 0 && (width * Bpp) % 16 == 0
-        && (new_w * Bpp) % 16 == 0 && width * Bpp <= 65000 && new_w * Bpp <= 65000;
+        && (new_w * Bpp) % 16 == 0 && width * Bpp <= 48000 && new_w * Bpp <= 65000;
 }
 
 bool resize_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
