@@ -307,3 +307,16 @@ def test_concurrent_callers_like_transcode_frame_threads(ac, chk):
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert not errors, errors
+
+
+def test_rows_wider_than_one_block(ac, chk):
+    """8K-class widths: rows are cut into column segments of 256 units (grid.z) in the 4:2:0 kernels."""
+    w, h = 7680 + 32, 6          # 482 units per row: one full segment + a partial one with a ragged last warp
+    for sf, df in [(F.IMG_YUV420P, F.IMG_RGB24), (F.IMG_YUV420P, F.IMG_BGRA32), (F.IMG_RGB24, F.IMG_YUV420P),
+                   (F.IMG_YUY2, F.IMG_YUV420P), (F.IMG_YUV420P, F.IMG_UYVY), (F.IMG_YUV444P, F.IMG_YUV420P),
+                   (F.IMG_YUV420P, F.IMG_YUV422P)]:
+        src = ck.random_frame(sf, w, h, seed=77)
+        got = ac.convert_batch(np.stack([src, src[::-1].copy()]), sf, df, w, h)
+        assert ac.lib.acgpu_last_kernel_tier() == 2
+        assert_same(got[0], chk.convert(src, sf, df, w, h, pad=0)[1], f"wide {F.NAMES[sf]}->{F.NAMES[df]}")
+        assert_same(got[1], chk.convert(src[::-1].copy(), sf, df, w, h, pad=0)[1], f"wide {F.NAMES[sf]}->{F.NAMES[df]} #2")

@@ -113,15 +113,17 @@ struct LaunchShape {
 // 4:2:0 mode: one block spans a row pair (ceil(upr/32) warps), grid.x strides over row pairs.
 inline LaunchShape shape_420(int upr, int nrp, int nframes, int nwaves = 32)
 {
+    // block = up to 256 threads along the row; wider rows (> 4096 pixels) are cut into column segments (grid.z)
     LaunchShape s;
-    const int threads = ((upr + 31) / 32) * 32;
+    const int threads = upr >= 256 ? 256 : ((upr + 31) / 32) * 32;
+    const int segs = (upr + threads - 1) / threads;
     s.block = dim3(threads);
     const int per_sm = 2048 / threads;
     long want = (long)sm_count() * per_sm * waves(nwaves);
-    long gx = (want + nframes - 1) / nframes;
+    long gx = (want + (long)nframes * segs - 1) / ((long)nframes * segs);
     if (gx < 1) gx = 1;
     if (gx > nrp) gx = nrp;
-    s.grid = dim3((unsigned)gx, (unsigned)nframes);
+    s.grid = dim3((unsigned)gx, (unsigned)nframes, (unsigned)segs);
     return s;
 }
 

@@ -197,9 +197,10 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
 
     if (SRC == S420) {
         const uint8_t *Y = p.s0 + soff, *U = p.s1 + soff, *V = p.s2 + soff;
-        const int unit = threadIdx.x;
+        const int unit = blockIdx.z * blockDim.x + threadIdx.x;          // blockIdx.z: column segment of wide rows
+        const int wu0 = blockIdx.z * blockDim.x + warp * 32;             // first unit of this warp
         const bool valid = unit < p.upr;
-        const int nvalid = min(32, p.upr - warp * 32);
+        const int nvalid = min(32, p.upr - wu0);
         if (nvalid <= 0) return;
         for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
             uint32_t y0[4] = {0, 0, 0, 0}, y1[4] = {0, 0, 0, 0};
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
                 uu = ldg64(U + co);
                 vv = ldg64(V + co);
             }
-            uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + warp * 512) * BPP;
+            uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + (size_t)wu0 * 16) * BPP;
             prefetch_dest_row<BPP>(row0, lane, nvalid);
             prefetch_dest_row<BPP>(row0 + (size_t)p.w * BPP, lane, nvalid);
             int cr[8], cg[8], cb[8];
@@ -325,9 +326,9 @@ __global__ void __launch_bounds__(256, 4) k_rgb2yuv(FastParams p)
     uint8_t *Y = p.d0 + doff, *U = p.d1 + doff, *V = p.d2 + doff;
 
     if (DST == D420) {
-        const uint32_t unit = threadIdx.x;
+        const uint32_t unit = blockIdx.z * blockDim.x + threadIdx.x;
         const bool valid = (int)unit < p.upr;
-        if (min(32, p.upr - warp * 32) <= 0) return;
+        if (p.upr - (int)(blockIdx.z * blockDim.x + warp * 32) <= 0) return;
         for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
             uint32_t px[16], ay[16];
             const uint8_t *row0 = src + (size_t)(2 * rp) * p.w * RI::bpp;
@@ -525,7 +526,7 @@ static bool fast_domain(const ConvertArgs &a, FastParams *out)
     const bool any420 = a.srcfmt == IMG_YUV420P || a.dstfmt == IMG_YUV420P;
     const size_t P = (size_t)w * h;
     if (any420) {
-        if (w % 16 || h % 2 || w / 16 > 256) return false;
+        if (w % 16 || h % 2) return false;
     } else {
         if (P % 16) return false;
         if ((a.srcfmt == IMG_YUV411P || a.dstfmt == IMG_YUV411P) && w % 4) return false;

@@ -37,11 +37,13 @@ __global__ void __launch_bounds__(256, 4) k_rowpair(FastParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *stage = s_stage + warp * 32 * OP::kStage;
     const size_t soff = (size_t)blockIdx.y * p.spitch, doff = (size_t)blockIdx.y * p.dpitch;
-    const int nvalid = min(32, p.upr - warp * 32);
+    const int unit = blockIdx.z * blockDim.x + threadIdx.x;              // blockIdx.z: column segment of wide rows
+    const int wu0 = blockIdx.z * blockDim.x + warp * 32;                 // first unit of this warp
+    const int nvalid = min(32, p.upr - wu0);
     if (nvalid <= 0) return;
-    const bool valid = (int)threadIdx.x < p.upr;
+    const bool valid = unit < p.upr;
     for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x)
-        OP::run(p, soff, doff, rp, (int)threadIdx.x, valid, warp, nvalid, stage, lane);
+        OP::run(p, soff, doff, rp, unit, valid, wu0, nvalid, stage, lane);
 }
 
 template <class OP>
@@ -368,14 +370,14 @@ template <int Q>
 struct P420ToPacked {
     static constexpr int kMode = MODE_ROWPAIR, kStage = 2;
     static __device__ __forceinline__ void run(const FastParams &p, size_t soff, size_t doff, int rp, int unit, bool valid,
-                                               int warp, int nvalid, uint4 *stage, int lane)
+                                               int wu0, int nvalid, uint4 *stage, int lane)
     {
         uint32_t yw[4], uw[2], vw[2], w[8];
         const size_t co = (size_t)rp * (p.w >> 1) + unit * 8;
         ld2(p.s1 + soff + co, valid, uw);
         ld2(p.s2 + soff + co, valid, vw);
         const uint8_t *Y = p.s0 + soff + (size_t)(2 * rp) * p.w + unit * 16;
-        uint8_t *out = p.d0 + doff + ((size_t)(2 * rp) * p.w + warp * 512) * 2;
+        uint8_t *out = p.d0 + doff + ((size_t)(2 * rp) * p.w + (size_t)wu0 * 16) * 2;
         ld4(Y, valid, yw);
         join_packed<Q>(yw, uw, vw, w);
         store_chunks<2>(stage, lane, w, out, nvalid);
