@@ -79,3 +79,31 @@ def test_convert_batch_matches_tcv_convert_semantics(ac, chk):
     assert np.array_equal(dd.download(), buf.download())
     assert ac.lib.acgpu_convert_batch(buf.ptr, dd.ptr, w, h, 0, sf, sfb, sfb, nf, None) == 0
     buf.free(); dd.free()
+
+
+@pytest.mark.parametrize("case", [
+    (F.IMG_YUV420P, F.IMG_RGB24, 1920, 1080, 9),      # several pipeline chunks (16 MB each)
+    (F.IMG_YUV420P, F.IMG_RGBA32, 320, 240, 5),       # alpha must survive the host round trip (dest is pre-loaded)
+    (F.IMG_YUY2, F.IMG_YUV420P, 1280, 720, 7),
+    (F.IMG_RGB24, F.IMG_YUV422P, 766, 512, 3),        # frame size not a multiple of 256: planes unaligned on device
+    (F.IMG_YV12, F.IMG_BGR24, 64, 16, 33),
+])
+def test_frames_host_pipeline(ac, chk, case):
+    """acgpu_imgconvert_frames_host: the end-to-end call bench.py times (pinned buffers, 3-slot pipeline)."""
+    sf, df, w, h, nf = case
+    sfb, dfb = F.frame_bytes(sf, w, h), F.frame_bytes(df, w, h)
+    hs, hd = ac.pinned(nf * sfb), ac.pinned(nf * dfb)
+    frames = [ck.random_frame(sf, w, h, seed=200 + i) for i in range(nf)]
+    for i in range(nf):
+        hs.array[i * sfb:(i + 1) * sfb] = frames[i]
+    hd.array[:] = 0x5A
+    ac._ok(ac.lib.acgpu_imgconvert_frames_host(hs.ptr, sf, hd.ptr, df, w, h, nf))
+    for i in range(nf):
+        want = chk.convert(frames[i], sf, df, w, h, prefill=0x5A, pad=0)[1]
+        assert np.array_equal(hd.array[i * dfb:(i + 1) * dfb], want), (case, i)
+    # pageable buffers work too (slower: the driver stages them)
+    src = np.concatenate(frames)
+    dst = np.full(nf * dfb, 0x5A, np.uint8)
+    ac._ok(ac.lib.acgpu_imgconvert_frames_host(src.ctypes.data, sf, dst.ctypes.data, df, w, h, nf))
+    assert np.array_equal(dst, np.asarray(hd.array))
+    hs.free(); hd.free()
