@@ -320,3 +320,33 @@ def test_rows_wider_than_one_block(ac, chk):
         assert ac.lib.acgpu_last_kernel_tier() == 2
         assert_same(got[0], chk.convert(src, sf, df, w, h, pad=0)[1], f"wide {F.NAMES[sf]}->{F.NAMES[df]}")
         assert_same(got[1], chk.convert(src[::-1].copy(), sf, df, w, h, pad=0)[1], f"wide {F.NAMES[sf]}->{F.NAMES[df]} #2")
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_bulk_async_staged_variants_are_bit_exact(mode):
+    """Tier 3b/3c (ACGPU_TMA=1/2: planar sources staged by cp.async.bulk + mbarrier, optionally bulk stores too) are
+    measured slower than tier 2 and not the default, but they stay selectable, so they stay tested.  The mode is read
+    once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import __graft_entry__ as e, checkers as ck
+F = ck.F
+pkg = e.load_package(); ac = pkg.AcGpu(); assert ac.ac_init(pkg.AC_CUDA) == 1
+chk = ck.best_checker()
+ac.lib.acgpu_force_tier(3)
+for (w, h, nf) in ((1920, 1080, 3), (1280, 720, 2), (64, 6, 5), (4128, 4, 2)):
+    for df in (F.IMG_RGB24, F.IMG_BGR24):
+        frames = np.stack([ck.random_frame(F.IMG_YUV420P, w, h, seed=300 + i) for i in range(nf)])
+        got = ac.convert_batch(frames, F.IMG_YUV420P, df, w, h)
+        assert ac.lib.acgpu_last_kernel_tier() == 3
+        for i in range(nf):
+            assert np.array_equal(got[i], chk.convert(frames[i], F.IMG_YUV420P, df, w, h, pad=0)[1]), (w, h, df, i)
+print("ok")
+""" % (entry.ROOT, os.path.join(entry.ROOT, "tests"))
+    env = dict(os.environ, ACGPU_TMA=mode)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

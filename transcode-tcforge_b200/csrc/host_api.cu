@@ -198,12 +198,14 @@ bool run_convert(const ConvertArgs &a)
     // Automatic order: vectorised tier, else generic.  Tier 3 (bulk/TMA stores) is selectable but NOT the default:
     // measured 3 % slower than tier 2 on the headline pair (profiles/r1_tier_ab.md).
     const int force = tls.force_tier;
+    tls.err[0] = 0;      // a tier that declines a call leaves this empty; a failed launch leaves its CUDA error
     if (force == 3) {
         if (convert_tma(a)) { tls.last_tier = 3; return true; }
-        set_error("tier 3 (bulk stores) does not cover this pair/size/alignment");
+        if (!tls.err[0]) set_error("tier 3 (bulk stores) does not cover this pair/size/alignment");
         return false;
     }
     if ((force == 0 || force == 2) && convert_fast(a)) { tls.last_tier = 2; return true; }
+    if (tls.err[0]) return false;                       // a launch failed: do not paper over it with another tier
     if (force == 2) { set_error("tier 2 (vectorised) does not cover this pair/size/alignment"); return false; }
     if (!convert_generic(a)) return false;
     tls.last_tier = 1;

@@ -16,6 +16,8 @@
 // convert_fast() returns false and the generic tier runs.
 #include "fast_common.cuh"
 
+#include <stdlib.h>
+
 namespace acgpu {
 namespace {
 
@@ -448,6 +450,113 @@ bool dispatch_yuv2rgb_dst(int dstfmt, const FastParams &p, int nframes, cudaStre
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tier 3b (experiment, selectable): YUV420P -> RGB24/BGR24 with the planar sources staged by bulk-async copies.
+// Each warp runs its own two-stage pipeline: lane 0 issues four cp.async.bulk (two luma row segments, one U and one V
+// segment: 512 + 512 + 256 + 256 bytes) for the NEXT row pair into shared memory, completion is signalled on a
+// per-stage mbarrier (expect_tx), and the warp converts the CURRENT row pair out of shared memory meanwhile.  The
+// loads therefore overlap the arithmetic without holding registers (the register-prefetch variant lost to
+// occupancy).  Output goes through the tier-2 transpose (LDS+STG) or, with BULKOUT, a bulk store.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool SWAP, bool BULKOUT>
+__global__ void __launch_bounds__(256, 4) k_yuv420_rgb24_tma(FastParams p)
+{
+    constexpr int BPP = 3;
+    __shared__ uint32_t s_tab[512];
+    extern __shared__ uint4 s_dyn[];
+    // per warp: 2 stages x 96 uint4 (y0: 32, y1: 32, u: 16, v: 16) + output staging (96 or 2 x 96 uint4) + 2 mbarriers
+    constexpr int kIn = 96, kOut = BULKOUT ? 192 : 96, kPerWarp = 2 * kIn + kOut + 1;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const uint32_t *>(&g_tabs16)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *wbase = s_dyn + warp * kPerWarp;
+    uint4 *in0 = wbase, *in1 = wbase + kIn, *stage = wbase + 2 * kIn;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + 2 * kIn + kOut);
+    const size_t soff = (size_t)blockIdx.y * p.spitch, doff = (size_t)blockIdx.y * p.dpitch;
+    const uint8_t *Y = p.s0 + soff, *U = p.s1 + soff, *V = p.s2 + soff;
+    uint8_t *dst = p.d0 + doff;
+    const int wu0 = blockIdx.z * blockDim.x + warp * 32;
+    const int nvalid = min(32, p.upr - wu0);
+    if (nvalid <= 0) return;
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t ybytes = (uint32_t)nvalid * 16, cbytes = (uint32_t)nvalid * 8;
+    auto issue = [&](int rp, int st) {       // lane 0 only
+        uint4 *b = st ? in1 : in0;
+        mbar_expect_tx(&bars[st], 2 * ybytes + 2 * cbytes);
+        const uint8_t *yp = Y + (size_t)(2 * rp) * p.w + (size_t)wu0 * 16;
+        bulk_load(b, yp, ybytes, &bars[st]);
+        bulk_load(b + 32, yp + p.w, ybytes, &bars[st]);
+        const size_t co = (size_t)rp * (p.w >> 1) + (size_t)wu0 * 8;
+        bulk_load(b + 64, U + co, cbytes, &bars[st]);
+        bulk_load(b + 80, V + co, cbytes, &bars[st]);
+    };
+    int rp = blockIdx.x;
+    if (rp < p.nrp && lane == 0) issue(rp, 0);
+    for (int it = 0; rp < p.nrp; rp += gridDim.x, it++) {
+        const int st = it & 1;
+        if (lane == 0 && rp + (int)gridDim.x < p.nrp) issue(rp + gridDim.x, st ^ 1);
+        mbar_wait(&bars[st], (it >> 1) & 1);
+        const uint4 *b = st ? in1 : in0;
+        const uint4 a = b[lane], c = b[32 + lane];
+        const uint2 uu = reinterpret_cast<const uint2 *>(b + 64)[lane], vv = reinterpret_cast<const uint2 *>(b + 80)[lane];
+        const uint32_t y0[4] = {a.x, a.y, a.z, a.w}, y1[4] = {c.x, c.y, c.z, c.w};
+        int cr[8], cg[8], cb[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            chroma_terms<S420>(reinterpret_cast<const int2 *>(s_tab), byte_of(s < 4 ? uu.x : uu.y, s & 3),
+                               byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+        uint32_t ow[12];
+        uint8_t *row0 = dst + ((size_t)(2 * rp) * p.w + (size_t)wu0 * 16) * BPP;
+        convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
+        if (BULKOUT) store_row_bulk<BPP>(stage, lane, ow, row0, nvalid);
+        else store_row_rgb<BPP, false>(stage, lane, ow, row0, nvalid);
+        convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
+        if (BULKOUT) store_row_bulk<BPP>(stage + 96, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+        else store_row_rgb<BPP, false>(stage, lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+        __syncwarp();        // every lane is done with this input stage before lane 0 refills it
+    }
+    if (BULKOUT && lane == 0) bulk_wait_all<0>();
+}
+
+template <bool SWAP, bool BULKOUT>
+bool launch_yuv420_rgb24_tma(const FastParams &p, int nframes, cudaStream_t st)
+{
+    const LaunchShape s = shape_420(p.upr, p.nrp, nframes, 8);
+    const size_t smem = (size_t)(s.block.x / 32) * (2 * 96 + (BULKOUT ? 192 : 96) + 1) * sizeof(uint4);
+    if (smem > 48 * 1024
+        && !check(cudaFuncSetAttribute(k_yuv420_rgb24_tma<SWAP, BULKOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
+        return false;
+    k_yuv420_rgb24_tma<SWAP, BULKOUT><<<s.grid, s.block, smem, st>>>(p);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_yuv420_rgb24_tma");
+    return true;
+}
+
 template <int SRC>
 bool dispatch_yuv2rgb_bulk(int dstfmt, const FastParams &p, int nframes, cudaStream_t st)
 {
@@ -563,6 +672,14 @@ bool convert_tma(const ConvertArgs &a)
     if (a.dstfmt != IMG_RGB24 && a.dstfmt != IMG_BGR24) return false;
     FastParams p;
     if (!fast_domain(a, &p)) return false;
+    // $ACGPU_TMA: 0 = bulk stores only (default tier 3), 1 = bulk-async staged loads + LDS/STG stores,
+    //             2 = bulk-async staged loads + bulk stores.  Loads need an even number of units per warp (w % 32 == 0).
+    static const int mode = [] { const char *e = getenv("ACGPU_TMA"); return e ? atoi(e) : 0; }();
+    if (mode > 0 && a.srcfmt == IMG_YUV420P && a.w % 32 == 0) {
+        const bool swap = a.dstfmt == IMG_BGR24;
+        if (mode == 1) return swap ? launch_yuv420_rgb24_tma<true, false>(p, a.nframes, a.stream) : launch_yuv420_rgb24_tma<false, false>(p, a.nframes, a.stream);
+        return swap ? launch_yuv420_rgb24_tma<true, true>(p, a.nframes, a.stream) : launch_yuv420_rgb24_tma<false, true>(p, a.nframes, a.stream);
+    }
     switch (a.srcfmt) {
     case IMG_YUV420P: return dispatch_yuv2rgb_bulk<S420>(a.dstfmt, p, a.nframes, a.stream);
     case IMG_YUV422P: return dispatch_yuv2rgb_bulk<S422>(a.dstfmt, p, a.nframes, a.stream);
