@@ -350,3 +350,19 @@ print("ok")
     env = dict(os.environ, ACGPU_TMA=mode)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_ac_init_selects_and_deselects_the_cuda_path(ac):
+    """aclib/accore.c:29-40 semantics with the new bit: the accel word is masked with ac_cpuinfo(); without AC_CUDA
+    there is nothing to run (libacgpu has no CPU implementation), and ac_init may be called again to switch back."""
+    src = np.zeros(F.frame_bytes(F.IMG_YUV420P, 64, 16), np.uint8)
+    assert ac.ac_cpuinfo() == pkg.AC_CUDA
+    try:
+        assert ac.ac_init(pkg.AC_NONE) == 0
+        assert "no CPU fallback" in ac.last_error()
+        assert ac.convert(src, F.IMG_YUV420P, F.IMG_RGB24, 64, 16)[0] == 0       # like the reference before ac_init
+        assert ac.ac_init(pkg.AC_SSE2) == 0                                       # an x86 bit alone selects nothing here
+    finally:
+        assert ac.ac_init(pkg.AC_ALL) == 1
+    assert ac.convert(src, F.IMG_YUV420P, F.IMG_RGB24, 64, 16)[0] == 1
+    assert ac.ac_init(pkg.AC_CUDA | pkg.AC_SSE2) == 1
