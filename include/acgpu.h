@@ -118,9 +118,9 @@ int acgpu_rescale(const uint8_t *src1, const uint8_t *src2, uint8_t *dest, size_
                   uint32_t weight1, uint32_t weight2, acgpu_stream_t stream);
 
 /* ---- frame-granular libtcvideo shapes (device-resident) ----------------------------------- */
-enum { ACGPU_DEINT_INTERPOLATE = 0, ACGPU_DEINT_LINEAR_BLEND = 1 };
-/* tcv_deinterlace INTERPOLATE / LINEAR_BLEND (libtcvideo/tcvideo.c:340-389) on nframes frames of
- * width x height x Bpp bytes.  Unlike the reference's linear blend, src is left intact. */
+enum { ACGPU_DEINT_INTERPOLATE = 0, ACGPU_DEINT_LINEAR_BLEND = 1, ACGPU_DEINT_DROP_FIELD_TOP = 2, ACGPU_DEINT_DROP_FIELD_BOTTOM = 3 };
+/* tcv_deinterlace (libtcvideo/tcvideo.c:290-389), all four modes, on nframes frames of width x height x Bpp bytes.
+ * The drop-field modes write height/2 rows (tcvideo.c:326-338).  Unlike the reference's linear blend, src is left intact. */
 int acgpu_deinterlace_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, int mode,
                             size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
 /* tcv_resize (libtcvideo/tcvideo.c:427-531): exactly one of resize_w / resize_h may be non-zero. */

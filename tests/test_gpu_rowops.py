@@ -118,3 +118,21 @@ def test_resize_rejects_what_tcv_resize_rejects(ac):
     for (w, h, bpp, rw, rh, sw, sh) in bad:
         assert ac.lib.acgpu_resize_batch(buf.ptr, buf.ptr, w, h, bpp, rw, rh, sw, sh, 0, 0, 1, None) == 0
     buf.free()
+
+
+@pytest.mark.parametrize("mode,first", [(2, 1), (3, 0)])
+def test_deinterlace_drop_field(ac, mode, first):
+    """tcvideo.c:326-338 -- drop top field keeps lines 1,3,5..., drop bottom keeps 0,2,4...; height/2 rows written."""
+    for (w, h, bpp) in [(1920, 1080, 1), (720, 577, 3), (50, 7, 3)]:
+        nf, bpl = 2, w * bpp
+        frames = np.stack([ck.splitmix_bytes(bpl * h, 80 + i) for i in range(nf)])
+        src = ac.malloc(nf * bpl * h).upload(frames.reshape(-1))
+        dst = ac.malloc(nf * bpl * h).fill(0x55)
+        ac._ok(ac.lib.acgpu_deinterlace_batch(src.ptr, dst.ptr, w, h, bpp, mode, bpl * h, bpl * h, nf, None))
+        ac.sync()
+        got = dst.download().reshape(nf, h, bpl)
+        for i in range(nf):
+            want = frames[i].reshape(h, bpl)[first::2][: h // 2]
+            assert np.array_equal(got[i, : h // 2], want)
+            assert (got[i, h // 2:] == 0x55).all()
+        src.free(); dst.free()

@@ -806,8 +806,20 @@ int acgpu_deinterlace_batch(const uint8_t *src, uint8_t *dest, int width, int he
 {
     // libtcvideo/tcvideo.c:290-311 argument checks
     if (!src || !dest || width <= 0 || height <= 0 || (Bpp != 1 && Bpp != 3)) { set_error("acgpu_deinterlace_batch: invalid frame parameters"); return 0; }
-    if (mode != ACGPU_DEINT_INTERPOLATE && mode != ACGPU_DEINT_LINEAR_BLEND) { set_error("acgpu_deinterlace_batch: invalid mode %d", mode); return 0; }
+    if (mode < ACGPU_DEINT_INTERPOLATE || mode > ACGPU_DEINT_DROP_FIELD_BOTTOM) { set_error("acgpu_deinterlace_batch: invalid mode %d", mode); return 0; }
     const int64_t Bpl = (int64_t)width * Bpp;
+    if (mode == ACGPU_DEINT_DROP_FIELD_TOP || mode == ACGPU_DEINT_DROP_FIELD_BOTTOM) {
+        // tcvideo.c:326-338: keep every other line, starting at line 1 when the top field is dropped
+        std::vector<acgpu_rowop> ops((size_t)(height / 2));
+        for (int y = 0; y < height / 2; y++) {
+            acgpu_rowop o{};
+            o.op = ACGPU_ROW_COPY;
+            o.src1_off = (int64_t)(2 * y + (mode == ACGPU_DEINT_DROP_FIELD_TOP ? 1 : 0)) * Bpl;
+            o.dest_off = y * Bpl;
+            ops[(size_t)y] = o;
+        }
+        return acgpu_rowops_run(src, spitch, dest, dpitch, ops.data(), height / 2, (int)Bpl, nframes, stream);
+    }
     std::vector<acgpu_rowop> ops((size_t)height);
     for (int y = 0; y < height; y++) {
         acgpu_rowop o{};
