@@ -31,7 +31,7 @@ constexpr int kPipeSlots = 3;
 
 struct Blob {               // small device-resident tables cached by content (row-op lists, weights)
     uint64_t hash;
-    size_t   bytes;
+    std::vector<uint8_t> host;   // the content itself: a hash match alone is not trusted
     void    *dptr;
 };
 
@@ -54,6 +54,27 @@ struct ThreadCtx {
     uint64_t launches = 0;
     int      last_tier = 0;
     int      force_tier = 0;
+
+    // A caller thread that exits gives its stream, staging buffers and cached tables back.  Best effort: at process
+    // exit the CUDA runtime may already be gone, in which case these calls fail harmlessly.
+    ~ThreadCtx()
+    {
+        for (int d = 0; d < kMaxDev; d++) {
+            DevCtx &c = dev[d];
+            if (!c.stream && !c.arena && !c.bounce && c.blobs.empty() && !c.pipe_stream[0]) continue;
+            if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (c.stream) cudaStreamSynchronize(c.stream);
+            for (int s = 0; s < kPipeSlots; s++) {
+                if (c.pipe_stream[s]) { cudaStreamSynchronize(c.pipe_stream[s]); cudaStreamDestroy(c.pipe_stream[s]); }
+                if (c.pipe_buf[s]) cudaFree(c.pipe_buf[s]);
+            }
+            for (Blob &b : c.blobs) cudaFree(b.dptr);
+            if (c.arena) cudaFree(c.arena);
+            if (c.bounce) cudaFreeHost(c.bounce);
+            if (c.stream) cudaStreamDestroy(c.stream);
+            cudaGetLastError();
+        }
+    }
 };
 
 thread_local ThreadCtx tls;
@@ -196,7 +217,7 @@ bool overwrites_whole_dest(int sfmt, int dfmt, int w, int h)
 bool run_convert(const ConvertArgs &a)
 {
     // Automatic order: vectorised tier, else generic.  Tier 3 (bulk/TMA stores) is selectable but NOT the default:
-    // measured 3 % slower than tier 2 on the headline pair (profiles/r1_tier_ab.md).
+    // measured 2-3 % slower than tier 2 on the headline pair (profiles/r1_experiments.md).
     const int force = tls.force_tier;
     tls.err[0] = 0;      // a tier that declines a call leaves this empty; a failed launch leaves its CUDA error
     if (force == 3) {
@@ -312,7 +333,7 @@ void *device_blob(DevCtx *c, const void *host, size_t bytes, cudaStream_t st)
 {
     const uint64_t h = fnv1a(host, bytes);
     for (const Blob &b : c->blobs)
-        if (b.hash == h && b.bytes == bytes) return b.dptr;
+        if (b.hash == h && b.host.size() == bytes && memcmp(b.host.data(), host, bytes) == 0) return b.dptr;
     if (c->blobs.size() >= 64) {
         cudaStreamSynchronize(c->stream);
         cudaDeviceSynchronize();
@@ -327,7 +348,11 @@ void *device_blob(DevCtx *c, const void *host, size_t bytes, cudaStream_t st)
         cudaFree(d);
         return nullptr;
     }
-    c->blobs.push_back({h, bytes, d});
+    Blob nb;
+    nb.hash = h;
+    nb.host.assign(static_cast<const uint8_t *>(host), static_cast<const uint8_t *>(host) + bytes);
+    nb.dptr = d;
+    c->blobs.push_back(std::move(nb));
     return d;
 }
 
