@@ -10,7 +10,7 @@
  * Prints one JSON object on stdout.  Used by bench.py's cpu_baseline leg and `--impl reference`.
  *
  * usage: cpubench LIB [--oracle] [--accel N] --op convert --src FMT --dst FMT -w W -h H
- *                 [--frames F] [--threads T] [--seconds S]
+ *                 [--frames F (distinct frames per thread, default 4)] [--threads T] [--seconds S]
  *        cpubench LIB ... --op average|rescale  (row-blend a W*H*bpp plane; --bpp 1|3)
  */
 #define _GNU_SOURCE
@@ -35,6 +35,7 @@ static rescale_fn f_rescale;
 static int srcfmt = 0x1001, dstfmt = 0x2001, W = 1920, H = 1080, bpp = 1;
 static const char *op = "convert";
 static double seconds = 2.0;
+static int nbuf = 4;      /* distinct frames each thread cycles through (streams from memory like a real frame queue) */
 static volatile int stop_flag;
 
 static double now(void)
@@ -91,20 +92,28 @@ static void *worker(void *arg)
     long i;
     if (!strcmp(op, "convert")) {
         long sb = frame_bytes(srcfmt, W, H), db = frame_bytes(dstfmt, W, H);
-        uint8_t *s = malloc(sb + 64), *s2 = malloc(sb + 64), *d = malloc(db + 64);
+        uint8_t *s = malloc(sb + 64), **s2 = malloc(sizeof(*s2) * nbuf), **d = malloc(sizeof(*d) * nbuf);
         uint8_t *sp[3], *dp[3];
+        int k, cur = 0;
         for (i = 0; i < sb; i++) s[i] = (uint8_t)sm64(&seed);
-        planes(sp, s2, srcfmt, W, H);
-        planes(dp, d, dstfmt, W, H);
-        memset(d, 0x55, db);
+        for (k = 0; k < nbuf; k++) {
+            s2[k] = malloc(sb + 64);
+            d[k] = malloc(db + 64);
+            memcpy(s2[k], s, sb);
+            s2[k][k % sb] ^= (uint8_t)(k + 1);       /* distinct frames */
+            memset(d[k], 0x55, db);
+        }
         /* UYVY/YVYU sources are rewritten in place by the reference: refresh src each frame only then */
         int refresh = (srcfmt == 0x1007 || srcfmt == 0x1008);
-        memcpy(s2, s, sb);
         while (!stop_flag) {
-            if (refresh) memcpy(s2, s, sb);
+            if (refresh) memcpy(s2[cur], s, sb);
+            planes(sp, s2[cur], srcfmt, W, H);
+            planes(dp, d[cur], dstfmt, W, H);
             f_convert(sp, srcfmt, dp, dstfmt, W, H);
             wk->frames++;
+            if (++cur == nbuf) cur = 0;
         }
+        for (k = 0; k < nbuf; k++) { free(s2[k]); free(d[k]); }
         free(s); free(s2); free(d);
     } else {
         long Bpl = (long)W * bpp, n = Bpl * H;
@@ -149,6 +158,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--bpp") && i + 1 < argc) bpp = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--seconds") && i + 1 < argc) seconds = atof(argv[++i]);
+        else if (!strcmp(argv[i], "--frames") && i + 1 < argc) nbuf = atoi(argv[++i]) > 0 ? atoi(argv[i]) : 1;
         else { fprintf(stderr, "cpubench: bad argument %s\n", argv[i]); return 2; }
     }
     if (threads < 1) threads = 1;
