@@ -203,7 +203,8 @@ def run_reference(args, kind, a, b, w, h, name):
     libs = cpu_libs()
     lib, accel, kd, is_o = libs["stock"]
     cores = os.cpu_count() or 1
-    per_step = 1.0
+    # a step = a bounded slice of frame-parallel conversion; the whole run stays near two minutes whatever K and W are
+    per_step = max(0.2, min(1.0, 120.0 / max(1, args.steps + args.warmup)))
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpubench(lib, accel, cores, per_step, kind, a, b, w, h, oracle=is_o)
