@@ -366,3 +366,13 @@ def test_ac_init_selects_and_deselects_the_cuda_path(ac):
         assert ac.ac_init(pkg.AC_ALL) == 1
     assert ac.convert(src, F.IMG_YUV420P, F.IMG_RGB24, 64, 16)[0] == 1
     assert ac.ac_init(pkg.AC_CUDA | pkg.AC_SSE2) == 1
+
+
+def test_colour_bars_round_trip_exactly_on_the_gpu(ac):
+    """testsuite/newtest.pl:544-566 (test_raw_raw_csp): YUV420P bars <-> RGB24 bars must be exact both ways."""
+    for (w, h) in [(704, 576), (720, 480), (1920, 1080), (64, 64)]:
+        yuv, rgb = ck.colour_bars_yuv420p(w, h), ck.colour_bars_rgb24(w, h)
+        assert np.array_equal(ac.convert_batch(yuv[None, :], F.IMG_YUV420P, F.IMG_RGB24, w, h)[0], rgb)
+        assert np.array_equal(ac.convert_batch(rgb[None, :], F.IMG_RGB24, F.IMG_YUV420P, w, h)[0], yuv)
+        ok, got = ac.convert(yuv, F.IMG_YUV420P, F.IMG_RGB24, w, h, pad=0)
+        assert ok == 1 and np.array_equal(got, rgb)
