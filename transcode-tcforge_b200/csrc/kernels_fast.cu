@@ -178,7 +178,7 @@ __device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32
 }
 
 template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK>
-__global__ void __launch_bounds__(256, 4) k_yuv2rgb(FastParams p)
+__global__ void __launch_bounds__(256, 5) k_yuv2rgb(FastParams p)   // 48 regs: measured best of 3..6 blocks (profiles/r1_experiments.md)
 {
     static_assert(!BULK || BPP == 3, "bulk stores cannot merge the untouched alpha byte");
     using SI = SrcInfo<SRC>;
