@@ -65,6 +65,7 @@ struct FastParams {
     int upr;           // 4:2:0 mode: 16-pixel units per row
     int nrp;           // 4:2:0 mode: row pairs
     uint32_t nunits;   // linear mode: units per frame
+    int flat420;       // 4:2:0 YUV->RGB: warps are packed across row-pair boundaries (no idle lanes when w/16 % 32 != 0)
 };
 
 // (a.b2, b.b2, c.b2, d.b2) -> one word
@@ -143,21 +144,24 @@ inline LaunchShape shape_linear(uint32_t nunits, int nframes, int nwaves = 32)
 
 // Writes one row's 16 pixels per lane (BPP*4 words) through the warp staging buffer to `rowbase`
 // (the address of the warp's first unit).  nvalid = number of lanes holding real units (warp-uniform).
+// Two-segment form: the first `ksplit` lanes' pixels continue at rowbase, the remaining lanes' pixels start at
+// `rowbase2` (a warp that straddles the end of an image row); the one-segment form passes ksplit = 32.
 template <int BPP, bool AFIRST>
-__device__ __forceinline__ void store_row_rgb(uint4 *stage, int lane, const uint32_t *ow, uint8_t *rowbase, int nvalid)
+__device__ __forceinline__ void store_row_rgb2(uint4 *stage, int lane, const uint32_t *ow, uint8_t *rowbase, uint8_t *rowbase2,
+                                               int ksplit, int nvalid)
 {
     constexpr int K = BPP;   // 16-byte chunks per lane
 #pragma unroll
     for (int k = 0; k < K; k++)
         stage[stage_slot<K>(lane, k)] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
     __syncwarp();
-    const int nchunks = nvalid * K;
+    const int nchunks = nvalid * K, csplit = ksplit * K;
 #pragma unroll
     for (int j = 0; j < K; j++) {
         const int c = j * 32 + lane;
         if (c < nchunks) {
             uint4 v = stage[stage_slot_linear<K>(c)];
-            uint8_t *g = rowbase + (size_t)c * 16;
+            uint8_t *g = c < csplit ? rowbase + (size_t)c * 16 : rowbase2 + (size_t)(c - csplit) * 16;
             if (BPP == 4) {     // keep the destination's alpha bytes (img_yuv_rgb.c:62-64 never stores them)
                 const uint4 old = *reinterpret_cast<const uint4 *>(g);
                 const uint32_t m = AFIRST ? 0x000000FFu : 0xFF000000u;
@@ -170,6 +174,12 @@ __device__ __forceinline__ void store_row_rgb(uint4 *stage, int lane, const uint
         }
     }
     __syncwarp();
+}
+
+template <int BPP, bool AFIRST>
+__device__ __forceinline__ void store_row_rgb(uint4 *stage, int lane, const uint32_t *ow, uint8_t *rowbase, int nvalid)
+{
+    store_row_rgb2<BPP, AFIRST>(stage, lane, ow, rowbase, rowbase, 32, nvalid);
 }
 
 enum RgbLayout { L_RGB24 = 0, L_BGR24 = 1, L_RGBA = 2, L_BGRA = 3, L_ARGB = 4, L_ABGR = 5 };

@@ -150,14 +150,20 @@ __device__ __forceinline__ void store_row_bulk(uint4 *buf, int lane, const uint3
 // 32-bit destinations are read-modify-written (alpha is kept).  Asking L2 for the destination tile at the top of
 // the iteration takes the DRAM read latency off the critical path between "pixels ready" and "store".
 template <int BPP>
-__device__ __forceinline__ void prefetch_dest_row(const uint8_t *rowbase, int lane, int nvalid)
+__device__ __forceinline__ void prefetch_dest_row2(const uint8_t *rowbase, const uint8_t *rowbase2, int ksplit, int lane, int nvalid)
 {
     if (BPP != 4) return;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int c = j * 32 + lane;
-        if (c < nvalid * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowbase + (size_t)c * 16));
+        if (c < nvalid * 4)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(c < ksplit * 4 ? rowbase + (size_t)c * 16 : rowbase2 + (size_t)(c - ksplit * 4) * 16));
     }
+}
+template <int BPP>
+__device__ __forceinline__ void prefetch_dest_row(const uint8_t *rowbase, int lane, int nvalid)
+{
+    prefetch_dest_row2<BPP>(rowbase, rowbase, 32, lane, nvalid);
 }
 
 template <int SRC>
@@ -177,8 +183,8 @@ __device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32
 #endif
 }
 
-template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK>
-__global__ void __launch_bounds__(256, 5) k_yuv2rgb(FastParams p)   // 48 regs: measured best of 3..6 blocks (profiles/r1_experiments.md)
+template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK, bool FLAT>
+__global__ void __launch_bounds__(256, FLAT ? 4 : 5) k_yuv2rgb(FastParams p)   // 48 regs: measured best of 3..6 blocks (profiles/r1_experiments.md)
 {
     static_assert(!BULK || BPP == 3, "bulk stores cannot merge the untouched alpha byte");
     using SI = SrcInfo<SRC>;
@@ -197,7 +203,52 @@ __global__ void __launch_bounds__(256, 5) k_yuv2rgb(FastParams p)   // 48 regs: 
     const size_t soff = (size_t)blockIdx.y * p.spitch, doff = (size_t)blockIdx.y * p.dpitch;
     uint8_t *dst = p.d0 + doff;
 
-    if (SRC == S420) {
+    if (SRC == S420 && FLAT) {
+        // Flat 4:2:0 mode: the (row pair, unit) grid is walked as one linear sequence, so every warp carries 32 real
+        // units even when the row does not fill whole warps (1080p: 120 units = 3.75 warps).  A warp may then straddle
+        // the end of a row pair: its first `k` lanes finish row pair A, the rest start row pair A+1, and the transposed
+        // store writes two segments.  No per-lane division: the warp's (rpA, uA) advance by constants each trip.
+        const uint8_t *Y = p.s0 + soff, *U = p.s1 + soff, *V = p.s2 + soff;
+        const uint32_t upr = (uint32_t)p.upr, total = (uint32_t)p.nrp * upr;
+        const uint32_t stride = gridDim.x * blockDim.x, qs = stride / upr, rs = stride - qs * upr;
+        uint32_t g0 = blockIdx.x * blockDim.x + warp * 32;
+        uint32_t rpA = g0 / upr, uA = g0 - rpA * upr;
+        const size_t rowb = (size_t)p.w * BPP;
+        for (; g0 < total; g0 += stride) {
+            const int nvalid = (int)min(32u, total - g0);
+            const int k = (int)min((uint32_t)nvalid, upr - uA);           // lanes that still belong to row pair A
+            uint32_t rp = rpA, unit = uA + lane;
+            if (unit >= upr) { unit -= upr; rp++; }
+            const bool valid = lane < nvalid;
+            uint32_t y0[4] = {0, 0, 0, 0}, y1[4] = {0, 0, 0, 0};
+            uint2 uu = make_uint2(0, 0), vv = make_uint2(0, 0);
+            if (valid) {
+                const uint8_t *yp = Y + (size_t)(2 * rp) * p.w + unit * 16;
+                const uint4 a = ldg128(yp), b = ldg128(yp + p.w);
+                y0[0] = a.x; y0[1] = a.y; y0[2] = a.z; y0[3] = a.w;
+                y1[0] = b.x; y1[1] = b.y; y1[2] = b.z; y1[3] = b.w;
+                const size_t co = (size_t)rp * (p.w >> 1) + unit * 8;
+                uu = ldg64(U + co);
+                vv = ldg64(V + co);
+            }
+            uint8_t *segA = dst + ((size_t)(2 * rpA) * p.w + (size_t)uA * 16) * BPP;
+            uint8_t *segB = dst + (size_t)(2 * (rpA + 1)) * rowb;
+            prefetch_dest_row2<BPP>(segA, segB, k, lane, nvalid);
+            prefetch_dest_row2<BPP>(segA + rowb, segB + rowb, k, lane, nvalid);
+            int cr[8], cg[8], cb[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                chroma_terms<SRC>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+            uint32_t ow[BPP * 4];
+            convert_row<SRC, SWAP, BPP, AFIRST>(y0, cr, cg, cb, ow);
+            store_row_rgb2<BPP, AFIRST>(stage, lane, ow, segA, segB, k, nvalid);
+            convert_row<SRC, SWAP, BPP, AFIRST>(y1, cr, cg, cb, ow);
+            store_row_rgb2<BPP, AFIRST>(stage, lane, ow, segA + rowb, segB + rowb, k, nvalid);
+            rpA += qs;
+            uA += rs;
+            if (uA >= upr) { uA -= upr; rpA++; }
+        }
+    } else if (SRC == S420) {
         const uint8_t *Y = p.s0 + soff, *U = p.s1 + soff, *V = p.s2 + soff;
         const int unit = blockIdx.z * blockDim.x + threadIdx.x;          // blockIdx.z: column segment of wide rows
         const int wu0 = blockIdx.z * blockDim.x + warp * 32;             // first unit of this warp
@@ -425,12 +476,29 @@ __global__ void __launch_bounds__(256, 4) k_rgb2yuv(FastParams p)
     }
 }
 
+inline bool flat420_enabled()
+{
+    static const bool on = [] { const char *e = getenv("ACGPU_FLAT420"); return !e || atoi(e) != 0; }();   // profiling knob
+    return on;
+}
+
 template <int SRC, bool SWAP, int BPP, bool AFIRST, bool BULK = false>
 bool launch_yuv2rgb(const FastParams &p, int nframes, cudaStream_t st)
 {
-    LaunchShape s = SRC == S420 ? shape_420(p.upr, p.nrp, nframes, 8) : shape_linear(p.nunits, nframes, 8);
+    FastParams q = p;
+    // Flat 4:2:0 mode packs warps across row-pair boundaries.  It costs registers (64 vs 48) and a two-segment store,
+    // so it only pays when the row-per-block shape would idle >20 % of the lanes: PAL 720 (45 units -> 64 lanes)
+    // 0.74 -> 0.84 of peak; 1280 (80 -> 96) break-even; 1920 / 3840 (120 -> 128, 240 -> 256) lose 6-8 % (measured).
+    // It needs at least a warp of units per row (a warp then straddles at most one row-pair boundary).
+    const int lanes_row = ((p.upr + 31) / 32) * 32;
+    q.flat420 = SRC == S420 && !BULK && p.upr >= 32 && p.upr * 10 < lanes_row * 8
+             && (uint64_t)p.upr * p.nrp < 0x7FFFFFFFu && flat420_enabled();
+    LaunchShape s = SRC != S420 ? shape_linear(p.nunits, nframes, 8)
+                  : q.flat420   ? shape_linear((uint32_t)(p.upr * p.nrp), nframes, 8)
+                                : shape_420(p.upr, p.nrp, nframes, 8);
     const size_t smem = (size_t)(s.block.x / 32) * 32 * BPP * sizeof(uint4) * (BULK ? 2 : 1);
-    k_yuv2rgb<SRC, SWAP, BPP, AFIRST, BULK><<<s.grid, s.block, smem, st>>>(p);
+    if (SRC == S420 && !BULK && q.flat420) k_yuv2rgb<SRC, SWAP, BPP, AFIRST, false, (SRC == S420 && !BULK)><<<s.grid, s.block, smem, st>>>(q);
+    else k_yuv2rgb<SRC, SWAP, BPP, AFIRST, BULK, false><<<s.grid, s.block, smem, st>>>(q);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_yuv2rgb");
     return true;
