@@ -389,3 +389,24 @@ def test_flat_420_mode_sizes(ac, chk):
             for i in range(nf):
                 want = chk.convert(frames[i], F.IMG_YUV420P, df, w, h, prefill=0x3C, pad=0)[1]
                 assert_same(got[i], want, f"flat420 {w}x{h} -> {F.NAMES[df]} frame {i}")
+
+
+RGB_ALL = (F.IMG_RGB24, F.IMG_BGR24, F.IMG_RGBA32, F.IMG_ABGR32, F.IMG_ARGB32, F.IMG_BGRA32)
+
+
+def test_ragged_420_widths_use_the_vectorised_tier(ac, chk):
+    """4:2:0 frames whose width is not a multiple of 16 (854x480, 1080-wide portrait, the reference test's 766):
+    rows are no longer 16-byte aligned, so YUV420P <-> RGB walks flat 16-pixel units and reaches the chroma rows with
+    byte-aligned accesses (S420R / D420R); units that run over the end of a row fetch/store sample by sample."""
+    sizes = [(854, 480, 1), (1080, 40, 2), (766, 32, 1), (40, 8, 3), (50, 16, 2), (18, 16, 2), (24, 2, 1), (426, 240, 1)]
+    for (w, h, nf) in sizes:
+        for rf in RGB_ALL:
+            for sf, df in ((F.IMG_YUV420P, rf), (rf, F.IMG_YUV420P), (F.IMG_YV12, rf), (rf, F.IMG_YV12)):
+                if (sf == F.IMG_YV12 or df == F.IMG_YV12) and rf not in (F.IMG_RGB24, F.IMG_ARGB32):
+                    continue
+                frames = np.stack([ck.random_frame(sf, w, h, seed=900 + i) for i in range(nf)])
+                got = ac.convert_batch(frames, sf, df, w, h, prefill=0xA5)
+                assert ac.lib.acgpu_last_kernel_tier() == 2, f"{F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h} fell back"
+                for i in range(nf):
+                    want = chk.convert(frames[i], sf, df, w, h, prefill=0xA5, pad=0)[1]
+                    assert_same(got[i], want, f"ragged {F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h} frame {i}")

@@ -20,6 +20,64 @@ __device__ __forceinline__ void stg128(uint8_t *p, uint4 v) { __stcs(reinterpret
 __device__ __forceinline__ void stg64(uint8_t *p, uint2 v) { __stcs(reinterpret_cast<uint2 *>(p), v); }
 __device__ __forceinline__ void stg32(uint8_t *p, uint32_t v) { __stcs(reinterpret_cast<uint32_t *>(p), v); }
 
+// ---- byte-aligned chroma access for ragged 4:2:0 rows (width % 16 != 0) ------------------------------------------
+// nb (1..8) bytes from an address with any alignment, returned in the low bytes.  Only the aligned 32-bit words that
+// hold requested bytes are touched, so the access never leaves the plane; bytes past nb are unspecified.
+__device__ __forceinline__ uint2 ldg_bytes8(const uint8_t *p, uint32_t nb)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t s = (uint32_t)(a & 3), sh = s * 8;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t w0 = __ldg(q), w1 = (4 - s < nb) ? __ldg(q + 1) : 0u, w2 = (8 - s < nb) ? __ldg(q + 2) : 0u;
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+__device__ __forceinline__ uint64_t u64_of(uint2 v) { return (uint64_t)v.x | ((uint64_t)v.y << 32); }
+__device__ __forceinline__ uint2 uint2_of(uint64_t v) { return make_uint2((uint32_t)v, (uint32_t)(v >> 32)); }
+
+// The 8 chroma samples of the 16 flat pixels that start at column x0 (even) of row y in a 4:2:0 frame of width w.
+// A unit that runs over the end of its row (at most one per row, w >= 16) takes its first k samples from chroma row
+// y/2 and the rest from the start of chroma row (y+1)/2.
+__device__ __forceinline__ uint2 gather420(const uint8_t *plane, uint32_t y, uint32_t x0, uint32_t w)
+{
+    const uint32_t cw = w >> 1, k = min(8u, (w - x0) >> 1);
+    uint2 v = ldg_bytes8(plane + (size_t)(y >> 1) * cw + (x0 >> 1), k);
+    if (k < 8) {
+        const uint2 t = ldg_bytes8(plane + (size_t)((y + 1) >> 1) * cw, 8 - k);
+        v = uint2_of((u64_of(v) & ((1ull << (8 * k)) - 1)) | (u64_of(t) << (8 * k)));
+    }
+    return v;
+}
+
+// 8 bytes to an address with any alignment, in the widest pieces the address allows (uniform along a row).
+__device__ __forceinline__ void stg64_unaligned(uint8_t *p, uint2 v)
+{
+    const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(p) & 7u;
+    if (a == 0) {
+        stg64(p, v);
+    } else if (a == 4) {
+        stg32(p, v.x);
+        stg32(p + 4, v.y);
+    } else if (!(a & 1)) {
+        uint16_t *h = reinterpret_cast<uint16_t *>(p);
+        h[0] = (uint16_t)v.x; h[1] = (uint16_t)(v.x >> 16); h[2] = (uint16_t)v.y; h[3] = (uint16_t)(v.y >> 16);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { p[i] = (uint8_t)(v.x >> (8 * i)); p[4 + i] = (uint8_t)(v.y >> (8 * i)); }
+    }
+}
+// bytes j0 .. j0+nb-1 of v to p[0 .. nb)
+__device__ __forceinline__ void stg_bytes8(uint8_t *p, uint2 v, uint32_t j0, uint32_t nb)
+{
+    if (nb == 8) {
+        stg64_unaligned(p, v);
+    } else {
+        const uint64_t x = u64_of(v) >> (8 * j0);
+#pragma unroll
+        for (uint32_t i = 0; i < 7; i++)
+            if (i < nb) p[i] = (uint8_t)(x >> (8 * i));
+    }
+}
+
 __device__ __forceinline__ uint32_t word_of(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int b) { return (w >> (8 * b)) & 0xFFu; }
 
@@ -55,7 +113,9 @@ __device__ __forceinline__ int stage_slot_linear(int c)   // c = global chunk in
     return stage_slot<K>(c / K, c % K);
 }
 
-enum SrcKind { S420 = 0, S422 = 1, S411 = 2, S444 = 3, SYUY2 = 4, SUYVY = 5, SYVYU = 6 };
+// S420R: 4:2:0 whose width is not a multiple of 16 ("ragged"): walked as flat 16-pixel units like the other layouts,
+// luma and RGB stay 16-byte aligned, only the chroma rows are reached through byte-aligned accesses.
+enum SrcKind { S420 = 0, S422 = 1, S411 = 2, S444 = 3, SYUY2 = 4, SUYVY = 5, SYVYU = 6, S420R = 7 };
 
 struct FastParams {
     const uint8_t *s0, *s1, *s2;
@@ -66,6 +126,7 @@ struct FastParams {
     int nrp;           // 4:2:0 mode: row pairs
     uint32_t nunits;   // linear mode: units per frame
     int flat420;       // 4:2:0 YUV->RGB: warps are packed across row-pair boundaries (no idle lanes when w/16 % 32 != 0)
+    int ragged420;     // 4:2:0 with width % 16 != 0: S420R / D420R kernels (flat units, byte-aligned chroma rows)
 };
 
 // (a.b2, b.b2, c.b2, d.b2) -> one word
@@ -183,7 +244,7 @@ __device__ __forceinline__ void store_row_rgb(uint4 *stage, int lane, const uint
 }
 
 enum RgbLayout { L_RGB24 = 0, L_BGR24 = 1, L_RGBA = 2, L_BGRA = 3, L_ARGB = 4, L_ABGR = 5 };
-enum YuvDst { D420 = 0, D422 = 1, D411 = 2, D444 = 3, DYUY2 = 4, DUYVY = 5, DYVYU = 6, DY8 = 7 };
+enum YuvDst { D420 = 0, D422 = 1, D411 = 2, D444 = 3, DYUY2 = 4, DUYVY = 5, DYVYU = 6, DY8 = 7, D420R = 8 };
 
 template <int SL> struct RgbInfo {
     static constexpr int bpp = SL <= L_BGR24 ? 3 : 4;

@@ -12,7 +12,8 @@
 // and the path is HBM-bound (DESIGN.md section 4 has the instruction budget that makes it so).
 //
 // Domain: every plane pointer and frame pitch 16-byte aligned, sizes on the formats' unit grid, and
-// width % 16 == 0 when a 4:2:0 plane is involved (otherwise (width*height) % 16 == 0).  Outside it
+// width % 16 == 0 when a 4:2:0 plane is involved (otherwise (width*height) % 16 == 0).  YUV420P <-> RGB also takes
+// any even width >= 16 with (width*height) % 16 == 0 through the ragged-row kernels (S420R / D420R).  Outside it
 // convert_fast() returns false and the generic tier runs.
 #include "fast_common.cuh"
 
@@ -75,7 +76,7 @@ constexpr int kBiasRB = ACGPU_LUT16 ? 4096 : 0, kBiasG = ACGPU_LUT16 ? 8192 : 0;
 //            destination chunk is read, merged with a byte mask, and written back (read-modify-write).
 
 template <int SRC> struct SrcInfo {
-    static constexpr bool packed = SRC >= SYUY2;
+    static constexpr bool packed = SRC >= SYUY2 && SRC <= SYVYU;
     static constexpr int nchroma = SRC == S444 ? 16 : SRC == S411 ? 4 : 8;   // chroma samples per 16 pixels
     static constexpr int yo = SRC == SUYVY ? 1 : 0;
     static constexpr int uo = SRC == SYUY2 ? 1 : SRC == SUYVY ? 0 : 3;
@@ -320,6 +321,18 @@ __global__ void __launch_bounds__(256, FLAT ? 4 : 5) k_yuv2rgb(FastParams p)   /
 #pragma unroll
                     for (int s = 0; s < 8; s++)
                         chroma_terms<SRC>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+                } else if (SRC == S420R) {
+                    // ragged 4:2:0: the unit's 16 flat pixels start at column x0 (even) of row y; their chroma samples sit
+                    // at an arbitrary byte of chroma row y/2 (and continue on the next row's when the unit wraps)
+                    uint2 uu = make_uint2(0, 0), vv = uu;
+                    if (valid) {
+                        const uint32_t w = (uint32_t)p.w, n = u * 16u, y = n / w, x0 = n - y * w;
+                        uu = gather420(S1, y, x0, w);
+                        vv = gather420(S2, y, x0, w);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 8; s++)
+                        chroma_terms<SRC>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
                 } else {   // S411
                     uint32_t uu = 0, vv = 0;
                     if (valid) { uu = ldg32(S1 + (size_t)u * 4); vv = ldg32(S2 + (size_t)u * 4); }
@@ -456,6 +469,28 @@ __global__ void __launch_bounds__(256, 4) k_rgb2yuv(FastParams p)
                 if (valid) {
                     stg32(U + (size_t)u * 4, pack_b2x4(ua[0], ua[1], ua[2], ua[3]));
                     stg32(V + (size_t)u * 4, pack_b2x4(va[0], va[1], va[2], va[3]));
+                }
+            } else if (DST == D420R) {
+                // ragged 4:2:0: the row decides what is sampled -- U from the even pixels of even rows, V from the odd
+                // pixels of odd rows -- and the samples land at an arbitrary byte of chroma row y/2.  A unit that wraps
+                // into row y+1 after k samples switches plane (and sampling phase) there.
+                if (valid) {
+                    using RI2 = RgbInfo<SL>;
+                    constexpr uint32_t ulo = RI2::half(-9714, -19070, 28784, 0), uhi = RI2::half(-9714, -19070, 28784, 2);
+                    constexpr uint32_t vlo = RI2::half(28784, -24103, -4681, 0), vhi = RI2::half(28784, -24103, -4681, 2);
+                    const uint32_t w = (uint32_t)p.w, cw = w >> 1, n = u * 16u, y = n / w, x0 = n - y * w;
+                    const uint32_t k = min(8u, (w - x0) >> 1);
+                    const bool oddA = y & 1;
+                    uint32_t c[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const bool odd = oddA != ((uint32_t)j >= k);
+                        const uint32_t s = odd ? px[2 * j + 1] : px[2 * j];
+                        c[j] = dp2a_hi_su(odd ? vhi : uhi, s, dp2a_lo_su(odd ? vlo : ulo, s, 32768u + (128u << 16)));
+                    }
+                    const uint2 v = make_uint2(pack_b2x4(c[0], c[1], c[2], c[3]), pack_b2x4(c[4], c[5], c[6], c[7]));
+                    stg_bytes8((oddA ? V : U) + (size_t)(y >> 1) * cw + (x0 >> 1), v, 0, k);
+                    if (k < 8) stg_bytes8((oddA ? U : V) + (size_t)((y + 1) >> 1) * cw, v, k, 8 - k);
                 }
             } else if (DST == D444) {
                 uint32_t ca[16];
@@ -638,7 +673,8 @@ bool dispatch_yuv2rgb_bulk(int dstfmt, const FastParams &p, int nframes, cudaStr
 bool fast_yuv2rgb(const ConvertArgs &a, const FastParams &p)
 {
     switch (a.srcfmt) {
-    case IMG_YUV420P: return dispatch_yuv2rgb_dst<S420>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV420P: return p.ragged420 ? dispatch_yuv2rgb_dst<S420R>(a.dstfmt, p, a.nframes, a.stream)
+                                         : dispatch_yuv2rgb_dst<S420>(a.dstfmt, p, a.nframes, a.stream);
     case IMG_YUV422P: return dispatch_yuv2rgb_dst<S422>(a.dstfmt, p, a.nframes, a.stream);
     case IMG_YUV411P: return dispatch_yuv2rgb_dst<S411>(a.dstfmt, p, a.nframes, a.stream);
     case IMG_YUV444P: return dispatch_yuv2rgb_dst<S444>(a.dstfmt, p, a.nframes, a.stream);
@@ -664,7 +700,7 @@ template <int SL>
 bool dispatch_rgb2yuv_dst(int dstfmt, const FastParams &p, int nframes, cudaStream_t st)
 {
     switch (dstfmt) {
-    case IMG_YUV420P: return launch_rgb2yuv<SL, D420>(p, nframes, st);
+    case IMG_YUV420P: return p.ragged420 ? launch_rgb2yuv<SL, D420R>(p, nframes, st) : launch_rgb2yuv<SL, D420>(p, nframes, st);
     case IMG_YUV422P: return launch_rgb2yuv<SL, D422>(p, nframes, st);
     case IMG_YUV411P: return launch_rgb2yuv<SL, D411>(p, nframes, st);
     case IMG_YUV444P: return launch_rgb2yuv<SL, D444>(p, nframes, st);
@@ -697,13 +733,25 @@ static bool fast_domain(const ConvertArgs &a, FastParams *out)
     const FmtDesc sd = describe(a.srcfmt), dd = describe(a.dstfmt);
     const int w = a.w, h = a.h;
     if (w <= 0 || h <= 0 || a.nframes <= 0) return false;
-    for (int i = 0; i < 3; i++)
-        if ((a.src.p[i] && !al16(a.src.p[i])) || (a.dst.p[i] && !al16(a.dst.p[i]))) return false;
     if (a.nframes > 1 && (a.src.pitch % 16 || a.dst.pitch % 16)) return false;
     const bool any420 = a.srcfmt == IMG_YUV420P || a.dstfmt == IMG_YUV420P;
     const size_t P = (size_t)w * h;
+    // every plane 16-byte aligned -- except the chroma planes of a ragged 4:2:0 frame, which are reached through
+    // byte-aligned accesses anyway (e.g. 50x16: V starts at byte 1000 of the frame)
+    const bool ragged_w = any420 && w % 16;
+    for (int i = 0; i < 3; i++) {
+        if (a.src.p[i] && !al16(a.src.p[i]) && !(ragged_w && i > 0 && a.srcfmt == IMG_YUV420P)) return false;
+        if (a.dst.p[i] && !al16(a.dst.p[i]) && !(ragged_w && i > 0 && a.dstfmt == IMG_YUV420P)) return false;
+    }
+    bool ragged = false;
     if (any420) {
-        if (w % 16 || h % 2) return false;
+        if (w % 2 || h % 2) return false;
+        if (w % 16) {
+            // ragged 4:2:0 rows: only the YUV420P <-> RGB kernels have a flat-unit form (S420R / D420R)
+            const bool other_rgb = (a.srcfmt == IMG_YUV420P ? dd.kind : sd.kind) == K_RGB && (a.srcfmt == IMG_YUV420P ? dd.bpp : sd.bpp) >= 3;
+            if (!other_rgb || w < 16 || P % 16 || P >= 0x7FFFFFFFu) return false;
+            ragged = true;
+        }
     } else {
         if (P % 16) return false;
         if ((a.srcfmt == IMG_YUV411P || a.dstfmt == IMG_YUV411P) && w % 4) return false;
@@ -717,6 +765,7 @@ static bool fast_domain(const ConvertArgs &a, FastParams *out)
     p.w = w; p.h = h;
     p.upr = w / 16; p.nrp = h / 2;
     p.nunits = (uint32_t)(P / 16);
+    p.ragged420 = ragged;
     *out = p;
     return true;
 }
@@ -739,7 +788,7 @@ bool convert_tma(const ConvertArgs &a)
 {
     if (a.dstfmt != IMG_RGB24 && a.dstfmt != IMG_BGR24) return false;
     FastParams p;
-    if (!fast_domain(a, &p)) return false;
+    if (!fast_domain(a, &p) || p.ragged420) return false;
     // $ACGPU_TMA: 0 = bulk stores only (default tier 3), 1 = bulk-async staged loads + LDS/STG stores,
     //             2 = bulk-async staged loads + bulk stores.  Loads need an even number of units per warp (w % 32 == 0).
     static const int mode = [] { const char *e = getenv("ACGPU_TMA"); return e ? atoi(e) : 0; }();
