@@ -623,6 +623,14 @@ int oracle_deinterlace(uint8_t *src, uint8_t *dest, int width, int height, int B
     int y;
     if (!src || !dest || width <= 0 || height <= 0 || (Bpp != 1 && Bpp != 3))
         return 0;
+    if (mode == 2 || mode == 3) {                     /* tcvideo.c:333-345: keep every second row (mode 2 drops the top field) */
+        const uint8_t *first = src + (mode == 2 ? Bpl : 0);
+        for (y = 0; y < height / 2; y++)
+            memmove(dest + (long)y * Bpl, first + (long)(2 * y) * Bpl, Bpl);
+        return 1;
+    }
+    if (mode != 0 && mode != 1)
+        return 0;
     interpolate_odd_rows(src, dest, Bpl, height);
     if (mode == 0)
         return 1;
@@ -687,5 +695,207 @@ int oracle_resize(const uint8_t *src, uint8_t *dest, int width, int height, int 
         }
     }
     free(tsrc); free(tw1); free(tw2);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Remaining element-wise libtcvideo operations.  One plane of width x     */
+/* height pixels, Bpp (1 or 3) bytes each, tightly packed.                                       */
+
+static int plane_args_ok(const uint8_t *src, const uint8_t *dest, int width, int height, int Bpp)
+{
+    return src && dest && width > 0 && height > 0 && (Bpp == 1 || Bpp == 3);
+}
+
+/* tcvideo.c:184-250.  Negative clip values grow the frame with `black`; values larger than the frame
+ * are folded into the opposite edge first (:204-219). */
+int oracle_clip(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp,
+                int left, int right, int top, int bottom, uint8_t black)
+{
+    int out_w, out_h, x0, y0, x, y, k;
+    if (!plane_args_ok(src, dest, width, height, Bpp))
+        return 0;
+    if (left + right >= width || top + bottom >= height)
+        return 0;
+    if (left > width)    { right += left - width;    left = width; }
+    if (right > width)   { left += right - width;    right = width; }
+    if (top > height)    { bottom += top - height;   top = height; }
+    if (bottom > height) { top += bottom - height;   bottom = height; }
+    out_w = width - left - right;
+    out_h = height - top - bottom;
+    /* Output pixel (x, y) shows source pixel (x + left, y + top) when that lies inside the source, else black.
+     * (The reference walks rows with memset/memcpy; the picture is the same.) */
+    x0 = left;
+    y0 = top;
+    for (y = 0; y < out_h; y++) {
+        const int sy = y + y0;
+        for (x = 0; x < out_w; x++) {
+            const int sx = x + x0;
+            uint8_t *d = dest + ((long)y * out_w + x) * Bpp;
+            if (sx >= 0 && sx < width && sy >= 0 && sy < height) {
+                for (k = 0; k < Bpp; k++)
+                    d[k] = src[((long)sy * width + sx) * Bpp + k];
+            } else {
+                for (k = 0; k < Bpp; k++)
+                    d[k] = black;
+            }
+        }
+    }
+    return 1;
+}
+
+/* tcvideo.c:681-717: keep every reduce_w-th pixel of every reduce_h-th row. */
+int oracle_reduce(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, int reduce_w, int reduce_h)
+{
+    int x, y, k;
+    const int out_w = reduce_w > 0 ? width / reduce_w : 0, out_h = reduce_h > 0 ? height / reduce_h : 0;
+    if (!plane_args_ok(src, dest, width, height, Bpp) || reduce_w <= 0 || reduce_h <= 0)
+        return 0;
+    if (reduce_w == 1 && reduce_h == 1) {             /* :713-715 whole-frame copy (keeps the full width*height) */
+        memmove(dest, src, (size_t)width * height * Bpp);
+        return 1;
+    }
+    if (reduce_w == 1) {                              /* :706-711 rows keep their full width */
+        for (y = 0; y < out_h; y++)
+            memmove(dest + (long)y * width * Bpp, src + (long)y * reduce_h * width * Bpp, (size_t)width * Bpp);
+        return 1;
+    }
+    for (y = 0; y < out_h; y++)                        /* :694-704 */
+        for (x = 0; x < out_w; x++)
+            for (k = 0; k < Bpp; k++)
+                dest[((long)y * out_w + x) * Bpp + k] = src[((long)y * reduce_h * width + (long)x * reduce_w) * Bpp + k];
+    return 1;
+}
+
+/* tcvideo.c:739-766 (rows mirrored top-bottom) and :787-818 (pixels mirrored left-right); src == dest is legal. */
+int oracle_flip_v(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp)
+{
+    const long Bpl = (long)width * Bpp;
+    long i;
+    int y;
+    if (!plane_args_ok(src, dest, width, height, Bpp))
+        return 0;
+    for (y = 0; y < (height + 1) / 2; y++) {
+        const uint8_t *a = src + y * Bpl, *b = src + (long)(height - 1 - y) * Bpl;
+        uint8_t *da = dest + y * Bpl, *db = dest + (long)(height - 1 - y) * Bpl;
+        for (i = 0; i < Bpl; i++) {
+            const uint8_t t = a[i];
+            da[i] = b[i];
+            db[i] = t;
+        }
+    }
+    return 1;
+}
+
+int oracle_flip_h(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp)
+{
+    int x, y, k;
+    if (!plane_args_ok(src, dest, width, height, Bpp))
+        return 0;
+    for (y = 0; y < height; y++) {
+        const uint8_t *s = src + (long)y * width * Bpp;
+        uint8_t *d = dest + (long)y * width * Bpp;
+        for (x = 0; x < (width + 1) / 2; x++) {
+            const int m = width - 1 - x;
+            for (k = 0; k < Bpp; k++) {
+                const uint8_t t = s[x * Bpp + k];
+                d[x * Bpp + k] = s[m * Bpp + k];
+                d[m * Bpp + k] = t;
+            }
+        }
+    }
+    return 1;
+}
+
+/* tcvideo.c:1180-1189: table[i] = (uint8_t)(pow(i/255, gamma) * 255), truncated. */
+void oracle_gamma_table(double gamma, uint8_t *table)
+{
+    int i;
+    for (i = 0; i < 256; i++)
+        table[i] = (uint8_t)(pow(i / 255.0, gamma) * 255);
+}
+
+int oracle_gamma_correct(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double gamma)
+{
+    uint8_t table[256];
+    long i, n = (long)width * height * Bpp;
+    if (!plane_args_ok(src, dest, width, height, Bpp) || gamma <= 0)
+        return 0;
+    oracle_gamma_table(gamma, table);
+    for (i = 0; i < n; i++)                            /* tcvideo.c:853-855 */
+        dest[i] = table[src[i]];
+    return 1;
+}
+
+/* tcvideo.c:1209-1224: 16.16 weights of the centre (c), left/right (x), up/down (y) and diagonal (d) taps;
+ * tables[0..255] = c, [256..511] = x, [512..767] = y, [768..1023] = d.  double -> uint32 truncates. */
+void oracle_aa_tables(double weight, double bias, uint32_t *tables)
+{
+    int i;
+    for (i = 0; i < 256; i++) {
+        tables[i] = i * weight * 65536;
+        tables[256 + i] = i * bias * (1 - weight) / 4 * 65536;
+        tables[512 + i] = i * (1 - bias) * (1 - weight) / 4 * 65536;
+        tables[768 + i] = (tables[256 + i] + tables[512 + i] + 1) / 2;
+    }
+}
+
+/* "same colour": the largest per-channel difference is below 25 (tcvideo.c:37,917-927) */
+static int aa_same(const uint8_t *p, const uint8_t *q, int Bpp)
+{
+    int k, worst = 0;
+    for (k = 0; k < Bpp; k++) {
+        const int d = abs((int)q[k] - (int)p[k]);
+        if (d > worst)
+            worst = d;
+    }
+    return worst < 25;
+}
+
+/* tcvideo.c:886-980.  Border pixels are copied.  An interior pixel is smoothed when its left (or right) neighbour
+ * matches exactly one of the vertical neighbours and differs from the other vertical one and from the opposite
+ * horizontal one (:945-949); the smoothed value is the 3x3 table-weighted sum + 32768, >> 16, in uint32. */
+int oracle_antialias(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double weight, double bias)
+{
+    uint32_t t[1024];
+    const long Bpl = (long)width * Bpp;
+    int x, y, k;
+    if (!plane_args_ok(src, dest, width, height, Bpp) || weight < 0 || weight > 1 || bias < 0 || bias > 1)
+        return 0;
+    oracle_aa_tables(weight, bias, t);
+    for (y = 0; y < height; y++) {
+        const uint8_t *row = src + y * Bpl;
+        uint8_t *out = dest + y * Bpl;
+        if (y == 0 || y == height - 1) {
+            memmove(out, row, (size_t)Bpl);
+            /* the reference copies the first and then the last row even when they are the same row (height 1), and a
+             * height-2 frame has no interior rows */
+            continue;
+        }
+        for (x = 0; x < width; x++) {
+            const uint8_t *c = row + (long)x * Bpp;
+            int smooth = 0;
+            if (x > 0 && x < width - 1) {
+                const uint8_t *l = c - Bpp, *r = c + Bpp, *u = c - Bpl, *d = c + Bpl;
+                const int lr = aa_same(l, r, Bpp);
+                smooth = (aa_same(l, u, Bpp) && !aa_same(l, d, Bpp) && !lr)
+                      || (aa_same(l, d, Bpp) && !aa_same(l, u, Bpp) && !lr)
+                      || (aa_same(r, u, Bpp) && !aa_same(r, d, Bpp) && !lr)
+                      || (aa_same(r, d, Bpp) && !aa_same(r, u, Bpp) && !lr);
+            }
+            for (k = 0; k < Bpp; k++) {
+                if (smooth) {
+                    const uint8_t *q = c + k;
+                    const uint32_t sum = t[768 + q[-Bpl - Bpp]] + t[512 + q[-Bpl]] + t[768 + q[-Bpl + Bpp]]
+                                       + t[256 + q[-Bpp]]       + t[q[0]]          + t[256 + q[Bpp]]
+                                       + t[768 + q[Bpl - Bpp]]  + t[512 + q[Bpl]]  + t[768 + q[Bpl + Bpp]]
+                                       + 32768;
+                    out[(long)x * Bpp + k] = (uint8_t)(sum >> 16);
+                } else {
+                    out[(long)x * Bpp + k] = c[k];
+                }
+            }
+        }
+    }
     return 1;
 }

@@ -5,6 +5,10 @@ Two checkers with one calling convention:
   * ``RefLib``  -- oracle/_ref/libac_ref_{c,sse2}.so, the unmodified reference compiled from
                    /root/reference/aclib by oracle/Makefile (present only where it was built;
                    the .so travels to the GPU box, /root/reference does not).
+and two with the libtcvideo calling convention (one plane, Bpp 1 or 3):
+  * ``Oracle``  again (oracle_deinterlace / resize / clip / reduce / flip / gamma / antialias);
+  * ``TcvRef``  -- oracle/_ref/libtcv_ref.so, the unmodified reference libtcvideo (tcvideo.c + zoom.c) over the
+                   plain-C aclib, with oracle/tcv_ref_stubs.c standing in for libtc's allocator and logger.
 Nothing under transcode-tcforge_b200/ imports this module.
 """
 from __future__ import annotations
@@ -91,8 +95,73 @@ def _bind(lib, prefix):
     return conv, avg, rs
 
 
-class Oracle(_Base):
+class _TcvOps:
+    """libtcvideo-shaped operations on one tightly packed plane (Bpp 1 or 3).  Subclasses provide ``_tcv(name)`` ->
+    callable(src_ptr, dest_ptr, *args) -> int.  Deinterlace modes use libacgpu's numbering: 0 interpolate,
+    1 linear blend, 2 drop top field, 3 drop bottom field."""
+
+    def _plane_op(self, name, src, out_bytes, *args, prefill=0x55, inplace=False):
+        s = np.array(src, dtype=np.uint8, copy=True)
+        d = s if inplace else np.full(max(out_bytes, 1), prefill, dtype=np.uint8)
+        ok = self._tcv(name)(_ptr(s), _ptr(d), *args)
+        return int(ok), d[:out_bytes] if not inplace else d
+
+    def deinterlace(self, src: np.ndarray, w: int, h: int, bpp: int, mode: int) -> np.ndarray:
+        rows = h // 2 if mode >= 2 else h
+        ok, d = self._plane_op("deinterlace", src, w * rows * bpp, w, h, bpp, mode)
+        assert ok == 1
+        return d
+
+    def resize(self, src: np.ndarray, w: int, h: int, bpp: int, rw: int, rh: int, sw: int, sh: int):
+        nw, nh = w + rw * sw, h + rh * sh
+        ok, d = self._plane_op("resize", src, nw * nh * bpp, w, h, bpp, rw, rh, sw, sh)
+        assert ok == 1
+        return d
+
+    def clip(self, src, w, h, bpp, left, right, top, bottom, black=0, prefill=0x55):
+        nw, nh = w - left - right, h - top - bottom
+        return self._plane_op("clip", src, max(nw, 0) * max(nh, 0) * bpp, w, h, bpp, left, right, top, bottom, black,
+                              prefill=prefill)
+
+    def reduce(self, src, w, h, bpp, rw, rh, prefill=0x55):
+        if rw <= 0 or rh <= 0:
+            n = w * h * bpp
+        elif rw == 1 and rh == 1:
+            n = w * h * bpp
+        elif rw == 1:
+            n = w * (h // rh) * bpp
+        else:
+            n = (w // rw) * (h // rh) * bpp
+        return self._plane_op("reduce", src, n, w, h, bpp, rw, rh, prefill=prefill)
+
+    def flip_v(self, src, w, h, bpp, inplace=False):
+        return self._plane_op("flip_v", src, w * h * bpp, w, h, bpp, inplace=inplace)
+
+    def flip_h(self, src, w, h, bpp, inplace=False):
+        return self._plane_op("flip_h", src, w * h * bpp, w, h, bpp, inplace=inplace)
+
+    def gamma(self, src, w, h, bpp, gamma):
+        return self._plane_op("gamma", src, w * h * bpp, w, h, bpp, float(gamma))
+
+    def antialias(self, src, w, h, bpp, weight, bias):
+        return self._plane_op("antialias", src, w * h * bpp, w, h, bpp, float(weight), float(bias))
+
+
+_TCV_SIGS = {   # argument types after (src, dest)
+    "deinterlace": [C.c_int] * 4,
+    "resize": [C.c_int] * 7,
+    "clip": [C.c_int] * 7 + [C.c_uint8],
+    "reduce": [C.c_int] * 5,
+    "flip_v": [C.c_int] * 3,
+    "flip_h": [C.c_int] * 3,
+    "gamma": [C.c_int] * 3 + [C.c_double],
+    "antialias": [C.c_int] * 3 + [C.c_double, C.c_double],
+}
+
+
+class Oracle(_Base, _TcvOps):
     name = "oracle"
+    _NAMES = {"gamma": "oracle_gamma_correct"}
 
     def __init__(self):
         path = os.path.join(ORACLE_DIR, "liboracle.so")
@@ -102,10 +171,15 @@ class Oracle(_Base):
         self._convert, self._average, self._rescale = _bind(self.lib, "oracle_")
         self.lib.oracle_resize_table.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
-        self.lib.oracle_deinterlace.restype = C.c_int
-        self.lib.oracle_deinterlace.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int]
-        self.lib.oracle_resize.restype = C.c_int
-        self.lib.oracle_resize.argtypes = [_u8p, _u8p] + [C.c_int] * 7
+        for op, sig in _TCV_SIGS.items():
+            fn = getattr(self.lib, self._NAMES.get(op, "oracle_" + op))
+            fn.restype = C.c_int
+            fn.argtypes = [_u8p, _u8p] + sig
+        self.lib.oracle_gamma_table.argtypes = [C.c_double, _u8p]
+        self.lib.oracle_aa_tables.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_uint32)]
+
+    def _tcv(self, op):
+        return getattr(self.lib, self._NAMES.get(op, "oracle_" + op))
 
     def resize_table(self, oldsize: int, newsize: int):
         n = newsize // 8
@@ -116,18 +190,54 @@ class Oracle(_Base):
         return (np.array(s[:n], dtype=np.int32), np.array(w1[:n], dtype=np.uint32),
                 np.array(w2[:n], dtype=np.uint32))
 
-    def deinterlace(self, src: np.ndarray, w: int, h: int, bpp: int, mode: int) -> np.ndarray:
-        s = np.array(src, dtype=np.uint8, copy=True)
-        d = np.full(w * h * bpp, 0x55, dtype=np.uint8)
-        assert self.lib.oracle_deinterlace(_ptr(s), _ptr(d), w, h, bpp, mode) == 1
-        return d
+    def gamma_table(self, gamma: float) -> np.ndarray:
+        t = np.zeros(256, np.uint8)
+        self.lib.oracle_gamma_table(float(gamma), _ptr(t))
+        return t
 
-    def resize(self, src: np.ndarray, w: int, h: int, bpp: int, rw: int, rh: int, sw: int, sh: int):
-        nw, nh = w + rw * sw, h + rh * sh
-        s = np.array(src, dtype=np.uint8, copy=True)
-        d = np.full(nw * nh * bpp, 0x55, dtype=np.uint8)
-        assert self.lib.oracle_resize(_ptr(s), _ptr(d), w, h, bpp, rw, rh, sw, sh) == 1
-        return d
+    def aa_tables(self, weight: float, bias: float) -> np.ndarray:
+        t = np.zeros(1024, np.uint32)
+        self.lib.oracle_aa_tables(float(weight), float(bias), t.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return t
+
+
+class TcvRef(_TcvOps):
+    """The unmodified reference libtcvideo (oracle/_ref/libtcv_ref.so); aclib inside it runs its plain-C path."""
+    name = "ref_tcv"
+    _NAMES = {"gamma": "tcv_gamma_correct"}
+    _MODES = {0: 2, 1: 3, 2: 0, 3: 1}    # libacgpu numbering -> TCVDeinterlaceMode (libtcvideo/tcvideo.h:29-34)
+
+    def __init__(self):
+        path = os.path.join(ORACLE_DIR, "_ref", "libtcv_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.ac_init.restype = C.c_int
+        self.lib.ac_init.argtypes = [C.c_int]
+        if self.lib.ac_init(0) != 1:
+            raise RuntimeError("reference ac_init failed")
+        self.lib.tcv_init.restype = C.c_void_p
+        self.handle = C.c_void_p(self.lib.tcv_init())
+        assert self.handle
+        for op, sig in _TCV_SIGS.items():
+            fn = getattr(self.lib, self._NAMES.get(op, "tcv_" + op))
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, _u8p, _u8p] + sig
+
+    def _tcv(self, op):
+        fn = getattr(self.lib, self._NAMES.get(op, "tcv_" + op))
+        if op == "deinterlace":
+            return lambda s, d, w, h, bpp, mode: fn(self.handle, s, d, w, h, bpp, self._MODES[mode])
+        return lambda s, d, *a: fn(self.handle, s, d, *a)
+
+
+def have_tcv_ref() -> bool:
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libtcv_ref.so"))
+
+
+def best_tcv_checker():
+    """The real libtcvideo when its build travelled with the repo, else the restatement."""
+    return TcvRef() if have_tcv_ref() else Oracle()
 
 
 class RefLib(_Base):

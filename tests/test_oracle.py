@@ -179,3 +179,56 @@ def test_oracle_matches_committed_golden_digests():
         assert ok == 1 and digest(got) == want, key
         n += 1
     assert n == 256 * 2
+
+
+# ---- libtcvideo-shaped plane operations -----------------------------------------------
+import tcv_cases  # noqa: E402
+
+TCV_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "tcv_digests.json")
+
+
+def test_oracle_tcv_ops_match_committed_reference_digests():
+    """Digests of the REFERENCE libtcvideo's outputs (tests/golden/make_golden_tcv.py, from oracle/_ref/libtcv_ref.so)."""
+    with open(TCV_GOLDEN) as f:
+        gold = json.load(f)
+    assert gold["generator"].startswith("oracle/_ref/libtcv_ref.so")
+    all_cases = tcv_cases.cases()
+    assert len(all_cases) == len(gold["digests"])
+    for case in all_cases:
+        want_ok, want = gold["digests"][case[0]]
+        ok, d = tcv_cases.run_case(ORACLE, case)
+        assert ok == want_ok, case[0]
+        if ok:
+            assert digest(d) == want, case[0]
+
+
+@pytest.mark.skipif(not ck.have_tcv_ref(), reason="oracle/_ref/libtcv_ref.so not built")
+def test_oracle_tcv_ops_match_reference_libtcvideo_directly():
+    ref = ck.TcvRef()
+    for case in tcv_cases.cases():
+        ok_r, d_r = tcv_cases.run_case(ref, case)
+        ok_o, d_o = tcv_cases.run_case(ORACLE, case)
+        assert ok_r == ok_o, case[0]
+        if ok_r:
+            assert np.array_equal(d_r, d_o), case[0]
+
+
+@pytest.mark.skipif(not ck.have_tcv_ref(), reason="oracle/_ref/libtcv_ref.so not built")
+def test_reference_resize_table_via_1080_to_720_rows():
+    """config 3 (iii): tcv_resize(…, 0, -45, 8, 8) on a 1080-row plane, reference vs restatement."""
+    ref = ck.TcvRef()
+    w, h = 64, 1080
+    src = ck.splitmix_bytes(w * h, 3)
+    assert np.array_equal(ref.resize(src, w, h, 1, 0, -45, 8, 8), ORACLE.resize(src, w, h, 1, 0, -45, 8, 8))
+    assert np.array_equal(ref.resize(src[: w * 720], w, 720, 1, 0, 45, 8, 8), ORACLE.resize(src[: w * 720], w, 720, 1, 0, 45, 8, 8))
+
+
+def test_antialias_cases_actually_smooth_something():
+    """Guards the case list: the blocky images must exercise the weighted 3x3 branch (tcvideo.c:950-966)."""
+    changed = 0
+    for case in tcv_cases.cases():
+        if case[1] == "antialias" and case[4] == "blocky" and case[3] == (0.333, 0.5):
+            _, _, (w, h, bpp), _, kind, seed = case
+            ok, d = tcv_cases.run_case(ORACLE, case)
+            changed += int((d != tcv_cases.image(kind, w, h, bpp, seed)).sum())
+    assert changed > 500
