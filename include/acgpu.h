@@ -137,6 +137,29 @@ int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, Imag
 int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t frame_pitch, int nframes,
                               acgpu_stream_t stream);
 
+/* ---- the remaining element-wise libtcvideo plane operations (device-resident) --------------------------------
+ * Same arguments, checks and return values (1 = success, 0 = rejected) as the reference functions they replace; one
+ * plane of width x height pixels with Bpp 1 or 3, nframes planes a fixed pitch apart, one launch per call. */
+/* tcv_clip (libtcvideo/tcvideo.c:184-250): negative clips grow the frame with black_pixel.  dest holds
+ * (width-clip_left-clip_right) x (height-clip_top-clip_bottom) pixels. */
+int acgpu_clip_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp,
+                     int clip_left, int clip_right, int clip_top, int clip_bottom, uint8_t black_pixel,
+                     size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+/* tcv_reduce (tcvideo.c:681-717): keeps every reduce_w-th pixel of every reduce_h-th row. */
+int acgpu_reduce_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, int reduce_w, int reduce_h,
+                       size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+/* tcv_flip_v / tcv_flip_h (tcvideo.c:739-766, 787-818); src == dest flips in place, as in the reference. */
+int acgpu_flip_v_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp,
+                       size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+int acgpu_flip_h_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp,
+                       size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+/* tcv_gamma_correct (tcvideo.c:840-858): the 256-entry table is built on the host exactly as :1180-1189 does. */
+int acgpu_gamma_correct_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double gamma,
+                              size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+/* tcv_antialias (tcvideo.c:886-980), weight tables as :1209-1224; src and dest must not overlap. */
+int acgpu_antialias_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double weight, double bias,
+                          size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

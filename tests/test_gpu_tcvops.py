@@ -1,0 +1,161 @@
+"""-m gpu parity for the element-wise libtcvideo plane operations on the device:
+acgpu_clip_batch / reduce / flip_v / flip_h / gamma_correct / antialias (+ deinterlace and resize replayed from the
+same case list) against the reference libtcvideo itself (oracle/_ref/libtcv_ref.so when it travelled with the repo,
+else the restatement) and against the committed digests of the reference's outputs."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+import checkers as ck
+import tcv_cases
+
+pkg = entry.load_package()
+pytestmark = pytest.mark.gpu
+
+OPS = {"gamma": "gamma_correct"}
+
+
+@pytest.fixture(scope="module")
+def ac():
+    a = pkg.AcGpu()
+    assert a.ac_init(pkg.AC_ALL) == 1, a.last_error()
+    return a
+
+
+@pytest.fixture(scope="module")
+def tcv():
+    return ck.best_tcv_checker()
+
+
+def out_bytes(op, w, h, bpp, args):
+    if op == "deinterlace":
+        return w * (h // 2 if args[0] >= 2 else h) * bpp
+    if op == "resize":
+        rw, rh, sw, sh = args
+        return (w + rw * sw) * (h + rh * sh) * bpp
+    if op == "clip":
+        return max(w - args[0] - args[1], 0) * max(h - args[2] - args[3], 0) * bpp
+    if op == "reduce":
+        rw, rh = args
+        if rw <= 0 or rh <= 0:
+            return 0
+        return w * (h // rh) * bpp if rw == 1 else (w // rw) * (h // rh) * bpp
+    return w * h * bpp
+
+
+def gpu_case(ac, case, nframes=1, gap=0):
+    key, op, (w, h, bpp), args, kind, seed = case
+    frames = np.stack([tcv_cases.image(kind, w, h, bpp, seed + 1000 * i) for i in range(nframes)])
+    inplace = op in ("flip_v", "flip_h") and args[0]
+    call_args = () if op in ("flip_v", "flip_h") else args
+    ok, got = ac.plane_op_batch(OPS.get(op, op), frames, out_bytes(op, w, h, bpp, args), w, h, bpp, *call_args,
+                                inplace=inplace, dst_gap=gap)
+    return ok, got, frames
+
+
+def test_case_list_matches_reference_digests_through_libacgpu(ac):
+    """Every case the reference libtcvideo was recorded on (tests/golden/tcv_digests.json), through the device."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tcv_digests.json")) as f:
+        gold = json.load(f)["digests"]
+    n = 0
+    for case in tcv_cases.cases():
+        want_ok, want = gold[case[0]]
+        if case[1] == "resize" and case[3][0] and case[3][1]:
+            continue
+        ok, got, _ = gpu_case(ac, case)
+        assert ok == want_ok, (case[0], ac.last_error())
+        if ok:
+            n_out = out_bytes(case[1], *case[2], case[3])
+            assert hashlib.sha256(got[0, :n_out].tobytes()).hexdigest()[:16] == want, case[0]
+            n += 1
+    assert n > 350
+
+
+def test_case_list_batched_with_gaps_against_the_checker(ac, tcv):
+    """Three frames per launch with a 48-byte gap between destination planes: frames are independent and the gap
+    stays untouched."""
+    for case in tcv_cases.cases():
+        key, op, (w, h, bpp), args, kind, seed = case
+        if op in ("deinterlace", "resize") or (op in ("flip_v", "flip_h") and args[0]):
+            continue
+        ok, got, frames = gpu_case(ac, case, nframes=3, gap=48)
+        n_out = out_bytes(op, w, h, bpp, args)
+        for i in range(3):
+            c2 = (key, op, (w, h, bpp), args, kind, seed + 1000 * i)
+            ok_r, want = tcv_cases.run_case(tcv, c2)
+            assert ok == ok_r, key
+            if ok:
+                assert np.array_equal(got[i, :n_out], want[:n_out]), (key, i)
+                assert (got[i, n_out:] == 0x55).all(), (key, "gap written")
+
+
+@pytest.mark.parametrize("bpp", [1, 3])
+def test_full_size_planes(ac, tcv, bpp):
+    """1920x1080 planes (vector paths) and 1918x1079 (byte paths) for every operation."""
+    for (w, h) in [(1920, 1080), (1918, 1079)]:
+        src = ck.splitmix_bytes(w * h * bpp, 5)
+        blocky = tcv_cases.blocky_image(w, h, bpp, 6)
+        f = src[None, :]
+        checks = [
+            ("clip", (8, 24, 4, 12, 16), tcv.clip(src, w, h, bpp, 8, 24, 4, 12, black=16)),
+            ("clip", (-16, -32, -2, -6, 128), tcv.clip(src, w, h, bpp, -16, -32, -2, -6, black=128)),
+            ("clip", (3, -5, -7, 9, 0), tcv.clip(src, w, h, bpp, 3, -5, -7, 9, black=0)),
+            ("reduce", (2, 2), tcv.reduce(src, w, h, bpp, 2, 2)),
+            ("reduce", (1, 2), tcv.reduce(src, w, h, bpp, 1, 2)),
+            ("reduce", (1, 1), tcv.reduce(src, w, h, bpp, 1, 1)),
+            ("reduce", (4, 3), tcv.reduce(src, w, h, bpp, 4, 3)),
+            ("flip_v", (), tcv.flip_v(src, w, h, bpp)),
+            ("flip_h", (), tcv.flip_h(src, w, h, bpp)),
+            ("gamma_correct", (2.2,), tcv.gamma(src, w, h, bpp, 2.2)),
+            ("gamma_correct", (0.45,), tcv.gamma(src, w, h, bpp, 0.45)),
+        ]
+        for op, args, (ok_r, want) in checks:
+            ok, got = ac.plane_op_batch(op, f, want.size, w, h, bpp, *args)
+            assert ok == ok_r == 1, (op, args, ac.last_error())
+            assert np.array_equal(got[0], want), (op, args, w, h, bpp)
+        for img in (src, blocky):
+            ok_r, want = tcv.antialias(img, w, h, bpp, 0.333, 0.5)
+            ok, got = ac.plane_op_batch("antialias", img[None, :], want.size, w, h, bpp, 0.333, 0.5)
+            assert ok == ok_r == 1 and np.array_equal(got[0], want)
+        # in-place flips (the reference allows src == dest: tcvideo.c:757-762, 806-814)
+        for op in ("flip_v", "flip_h"):
+            ok_r, want = getattr(tcv, op)(src, w, h, bpp, inplace=True)
+            ok, got = ac.plane_op_batch(op, f, want.size, w, h, bpp, inplace=True)
+            assert ok == 1 and np.array_equal(got[0], want), op
+
+
+def test_flips_are_involutions_and_commute(ac):
+    w, h, bpp = 1280, 720, 3
+    f = ck.splitmix_bytes(w * h * bpp, 9)[None, :]
+    _, v = ac.plane_op_batch("flip_v", f, f.size, w, h, bpp)
+    _, vv = ac.plane_op_batch("flip_v", v, f.size, w, h, bpp)
+    assert np.array_equal(vv, f)
+    _, hh = ac.plane_op_batch("flip_h", f, f.size, w, h, bpp)
+    _, hv = ac.plane_op_batch("flip_v", hh, f.size, w, h, bpp)
+    _, vh = ac.plane_op_batch("flip_h", v, f.size, w, h, bpp)
+    assert np.array_equal(hv, vh)
+    img = f.reshape(h, w, bpp)
+    assert np.array_equal(hv.reshape(h, w, bpp), img[::-1, ::-1])
+
+
+def test_rejections_match_the_reference(ac):
+    buf = ac.malloc(1 << 16)
+    L = ac.lib
+    assert L.acgpu_clip_batch(buf.ptr, buf.ptr, 64, 32, 2, 0, 0, 0, 0, 0, 0, 0, 1, None) == 0          # Bpp
+    assert L.acgpu_clip_batch(buf.ptr, buf.ptr, 64, 32, 1, 32, 32, 0, 0, 0, 0, 0, 1, None) == 0        # nothing left
+    assert L.acgpu_clip_batch(buf.ptr, buf.ptr, 64, 32, 1, 0, 0, 40, -8, 0, 0, 0, 1, None) == 0
+    assert L.acgpu_reduce_batch(buf.ptr, buf.ptr, 64, 32, 1, 0, 1, 0, 0, 1, None) == 0
+    assert L.acgpu_reduce_batch(None, buf.ptr, 64, 32, 1, 1, 1, 0, 0, 1, None) == 0
+    assert L.acgpu_flip_v_batch(buf.ptr, buf.ptr, 0, 32, 1, 0, 0, 1, None) == 0
+    assert L.acgpu_flip_h_batch(buf.ptr, buf.ptr, 64, -1, 3, 0, 0, 1, None) == 0
+    assert L.acgpu_gamma_correct_batch(buf.ptr, buf.ptr, 64, 32, 1, 0.0, 0, 0, 1, None) == 0
+    assert L.acgpu_gamma_correct_batch(buf.ptr, buf.ptr, 64, 32, 1, -2.0, 0, 0, 1, None) == 0
+    assert L.acgpu_antialias_batch(buf.ptr, buf.ptr + 4096, 64, 32, 1, 1.5, 0.5, 0, 0, 1, None) == 0
+    assert L.acgpu_antialias_batch(buf.ptr, buf.ptr + 4096, 64, 32, 1, 0.5, -0.5, 0, 0, 1, None) == 0
+    assert L.acgpu_antialias_batch(buf.ptr, buf.ptr, 64, 32, 1, 0.5, 0.5, 0, 0, 1, None) == 0          # overlap
+    assert b"overlap" in L.acgpu_last_error()
+    buf.free()

@@ -54,6 +54,8 @@ ABI_SYMBOLS = [
     "acgpu_event_sync", "acgpu_event_elapsed_ms", "acgpu_imgconvert_batch", "acgpu_imgconvert_frames_host",
     "acgpu_rowops_run", "acgpu_average", "acgpu_rescale", "acgpu_deinterlace_batch", "acgpu_resize_batch",
     "acgpu_convert_batch", "acgpu_decolor_rgb24_batch",
+    "acgpu_clip_batch", "acgpu_reduce_batch", "acgpu_flip_v_batch", "acgpu_flip_h_batch",
+    "acgpu_gamma_correct_batch", "acgpu_antialias_batch",
 ]
 
 
@@ -89,6 +91,12 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "acgpu_resize_batch": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, sz, sz, i32, vp]),
         "acgpu_convert_batch": (i32, [vp, vp, i32, i32, i32, i32, sz, sz, i32, vp]),
         "acgpu_decolor_rgb24_batch": (i32, [vp, i32, i32, sz, i32, vp]),
+        "acgpu_clip_batch": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, C.c_uint8, sz, sz, i32, vp]),
+        "acgpu_reduce_batch": (i32, [vp, vp, i32, i32, i32, i32, i32, sz, sz, i32, vp]),
+        "acgpu_flip_v_batch": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, vp]),
+        "acgpu_flip_h_batch": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, vp]),
+        "acgpu_gamma_correct_batch": (i32, [vp, vp, i32, i32, i32, C.c_double, sz, sz, i32, vp]),
+        "acgpu_antialias_batch": (i32, [vp, vp, i32, i32, i32, C.c_double, C.c_double, sz, sz, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -237,6 +245,27 @@ class AcGpu:
         return self.lib.acgpu_imgconvert_batch(_vp3([dsrc + o for o in so]), srcfmt, src_pitch,
                                                _vp3([ddst + o for o in do]), destfmt, dst_pitch,
                                                w, h, nframes, stream)
+
+    def plane_op_batch(self, op: str, frames: np.ndarray, out_bytes: int, w: int, h: int, bpp: int, *args,
+                       prefill: int = 0x55, inplace: bool = False, dst_gap: int = 0):
+        """Upload [nframes, w*h*bpp] planes, run ``acgpu_<op>_batch`` (clip / reduce / flip_v / flip_h / gamma_correct /
+        antialias / deinterlace / resize) once over the batch, download [nframes, out_bytes + dst_gap].
+        Returns ``(ok, planes)``; ``inplace`` passes the source buffer as destination."""
+        nf, sfb = frames.shape[0], w * h * bpp
+        fn = getattr(self.lib, f"acgpu_{op}_batch")
+        ds = self.malloc(nf * sfb).upload(np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1))
+        if inplace:
+            dd, dp = ds, sfb
+        else:
+            dp = out_bytes + dst_gap
+            dd = self.malloc(max(nf * dp, 1)).fill(prefill)
+        ok = fn(ds.ptr, dd.ptr, w, h, bpp, *args, sfb, dp, nf, None)
+        self.sync()
+        out = dd.download(nf * dp).reshape(nf, dp) if ok else None
+        ds.free()
+        if not inplace:
+            dd.free()
+        return int(ok), out
 
     def convert_batch(self, frames: np.ndarray, srcfmt: int, destfmt: int, w: int, h: int, prefill: int = 0x55,
                       src_pitch: int | None = None, dst_pitch: int | None = None) -> np.ndarray:

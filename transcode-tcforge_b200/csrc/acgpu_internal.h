@@ -84,6 +84,31 @@ bool resize_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpi
                      const int32_t *d_source, const uint32_t *d_w1, const uint32_t *d_w2,
                      int width, int new_w, int new_h, int Bpp, int scale_w, int nframes, cudaStream_t st);
 
+// libtcvideo plane operations (tcvops.cu).
+// Window copy: destination row y shows bytes [sxb, sxb+cn) of source row y*row_mul + row_add at its bytes [cl, cl+cn)
+// and the fill byte elsewhere (also in rows whose source row is outside [0, srows)).
+struct TcvWindow {
+    const uint8_t *src;
+    size_t   spitch;
+    uint8_t *dst;
+    size_t   dpitch;
+    uint32_t dBpl, sBpl;          // bytes per destination / source row
+    int      drows, srows;
+    int      row_mul, row_add;
+    uint32_t cl, cn, sxb;
+    uint32_t fill;                // fill byte replicated into all four bytes
+    int      vec;                 // set by the launcher: destination chunks are 16-byte aligned
+};
+bool tcv_window_launch(TcvWindow p, int nframes, cudaStream_t st);
+bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int ow, int oh, int rw, int rh,
+                       int Bpp, int nframes, cudaStream_t st);
+bool tcv_flip_v_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int h, int Bpp, int nframes, cudaStream_t st);
+bool tcv_flip_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int h, int Bpp, int nframes, cudaStream_t st);
+bool tcv_lut_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint8_t *d_table, size_t nbytes,
+                    int nframes, cudaStream_t st);
+bool tcv_antialias_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint32_t *d_tables, int w, int h,
+                          int Bpp, int nframes, cudaStream_t st);
+
 // Per-thread bookkeeping (host_api.cu).
 void     note_launch(int n = 1);
 void     set_error(const char *fmt, ...);

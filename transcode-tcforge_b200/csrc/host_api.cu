@@ -999,4 +999,128 @@ int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t pit
         && acgpu_imgconvert_batch(gray, IMG_GRAY8, gpitch, rgb, IMG_RGB24, pitch, width, height, nframes, stream);
 }
 
+// ---- the remaining element-wise libtcvideo operations ------------------------------------
+static bool plane_args_ok(const char *who, const void *src, const void *dest, int width, int height, int Bpp)
+{
+    // the check every tcv_* function opens with (e.g. libtcvideo/tcvideo.c:192-195)
+    if (!src || !dest || width <= 0 || height <= 0 || (Bpp != 1 && Bpp != 3)) { set_error("%s: invalid frame parameters", who); return false; }
+    if ((uint64_t)width * height * Bpp >= 0x7FFFFFF0ull) { set_error("%s: plane too large", who); return false; }
+    return true;
+}
+
+int acgpu_clip_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, int clip_left, int clip_right,
+                     int clip_top, int clip_bottom, uint8_t black_pixel, size_t spitch, size_t dpitch, int nframes,
+                     acgpu_stream_t stream)
+{
+    if (!plane_args_ok("acgpu_clip_batch", src, dest, width, height, Bpp)) return 0;
+    if ((int64_t)clip_left + clip_right >= width || (int64_t)clip_top + clip_bottom >= height) {   // tcvideo.c:196-202
+        set_error("acgpu_clip_batch: clipping parameters (%d,%d,%d,%d) invalid for frame size %dx%d", clip_top, clip_left,
+                  clip_bottom, clip_right, width, height);
+        return 0;
+    }
+    // tcvideo.c:204-219: a clip wider than the frame eats into the opposite (negative) border
+    if (clip_left > width)    { clip_right += clip_left - width;    clip_left = width; }
+    if (clip_right > width)   { clip_left += clip_right - width;    clip_right = width; }
+    if (clip_top > height)    { clip_bottom += clip_top - height;   clip_top = height; }
+    if (clip_bottom > height) { clip_top += clip_bottom - height;   clip_bottom = height; }
+    const int64_t new_w = (int64_t)width - clip_left - clip_right, new_h = (int64_t)height - clip_top - clip_bottom;
+    const int64_t copy_w = (int64_t)width - (clip_left < 0 ? 0 : clip_left) - (clip_right < 0 ? 0 : clip_right);
+    if (new_w * new_h * Bpp >= 0x7FFFFFF0ll) { set_error("acgpu_clip_batch: result too large"); return 0; }
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (nframes <= 0) return 1;
+    TcvWindow p{};
+    p.src = src; p.spitch = spitch; p.dst = dest; p.dpitch = dpitch;
+    p.dBpl = (uint32_t)(new_w * Bpp); p.sBpl = (uint32_t)width * Bpp;
+    p.drows = (int)new_h; p.srows = height;
+    p.row_mul = 1; p.row_add = clip_top;
+    p.cl = (uint32_t)((clip_left < 0 ? -(int64_t)clip_left : 0) * Bpp);
+    p.cn = (uint32_t)((copy_w > 0 ? copy_w : 0) * Bpp);
+    p.sxb = (uint32_t)((clip_left > 0 ? clip_left : 0) * Bpp);
+    p.fill = 0x01010101u * black_pixel;
+    return tcv_window_launch(p, nframes, pick_stream(c, stream)) ? 1 : 0;
+}
+
+int acgpu_reduce_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, int reduce_w, int reduce_h,
+                       size_t spitch, size_t dpitch, int nframes, acgpu_stream_t stream)
+{
+    if (!plane_args_ok("acgpu_reduce_batch", src, dest, width, height, Bpp)) return 0;
+    if (reduce_w <= 0 || reduce_h <= 0) { set_error("acgpu_reduce_batch: invalid reduction parameters (%d,%d)", reduce_w, reduce_h); return 0; }
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (nframes <= 0) return 1;
+    cudaStream_t st = pick_stream(c, stream);
+    if (reduce_w != 1)      // tcvideo.c:694-704
+        return tcv_reduce_launch(src, spitch, dest, dpitch, width, width / reduce_w, height / reduce_h, reduce_w, reduce_h, Bpp, nframes, st) ? 1 : 0;
+    // :706-715 whole rows: every reduce_h-th one, or (reduce_h == 1) the plain copy
+    TcvWindow p{};
+    p.src = src; p.spitch = spitch; p.dst = dest; p.dpitch = dpitch;
+    p.dBpl = p.sBpl = (uint32_t)width * Bpp;
+    p.drows = height / reduce_h; p.srows = height;
+    p.row_mul = reduce_h; p.row_add = 0;
+    p.cl = 0; p.cn = p.dBpl; p.sxb = 0;
+    return tcv_window_launch(p, nframes, st) ? 1 : 0;
+}
+
+int acgpu_flip_v_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, size_t spitch, size_t dpitch,
+                       int nframes, acgpu_stream_t stream)
+{
+    if (!plane_args_ok("acgpu_flip_v_batch", src, dest, width, height, Bpp)) return 0;
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (nframes <= 0) return 1;
+    return tcv_flip_v_launch(src, spitch, dest, dpitch, width, height, Bpp, nframes, pick_stream(c, stream)) ? 1 : 0;
+}
+
+int acgpu_flip_h_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, size_t spitch, size_t dpitch,
+                       int nframes, acgpu_stream_t stream)
+{
+    if (!plane_args_ok("acgpu_flip_h_batch", src, dest, width, height, Bpp)) return 0;
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (nframes <= 0) return 1;
+    return tcv_flip_h_launch(src, spitch, dest, dpitch, width, height, Bpp, nframes, pick_stream(c, stream)) ? 1 : 0;
+}
+
+int acgpu_gamma_correct_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double gamma,
+                              size_t spitch, size_t dpitch, int nframes, acgpu_stream_t stream)
+{
+    if (!plane_args_ok("acgpu_gamma_correct_batch", src, dest, width, height, Bpp)) return 0;
+    if (!(gamma > 0)) { set_error("acgpu_gamma_correct_batch: invalid gamma (%.3f)", gamma); return 0; }   // tcvideo.c:848-851
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (nframes <= 0) return 1;
+    cudaStream_t st = pick_stream(c, stream);
+    uint8_t table[256];
+    for (int i = 0; i < 256; i++) table[i] = (uint8_t)(pow((i / 255.0), gamma) * 255);    // tcvideo.c:1180-1189, host doubles
+    const uint8_t *d_table = static_cast<const uint8_t *>(device_blob(c, table, sizeof(table), st));
+    if (!d_table) return 0;
+    return tcv_lut_launch(src, spitch, dest, dpitch, d_table, (size_t)width * height * Bpp, nframes, st) ? 1 : 0;
+}
+
+int acgpu_antialias_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double weight, double bias,
+                          size_t spitch, size_t dpitch, int nframes, acgpu_stream_t stream)
+{
+    if (!plane_args_ok("acgpu_antialias_batch", src, dest, width, height, Bpp)) return 0;
+    if (!(weight >= 0 && weight <= 1 && bias >= 0 && bias <= 1)) {                       // tcvideo.c:899-903
+        set_error("acgpu_antialias_batch: invalid antialiasing parameters (weight=%.3f, bias=%.3f)", weight, bias);
+        return 0;
+    }
+    if (src == dest) { set_error("acgpu_antialias_batch: src and dest must not overlap (a 3x3 neighbourhood is read)"); return 0; }
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (nframes <= 0) return 1;
+    cudaStream_t st = pick_stream(c, stream);
+    uint32_t t[1024];     // c | x | y | d, tcvideo.c:1209-1224 (double -> uint32 truncation, evaluation order kept)
+    for (int i = 0; i < 256; i++) {
+        t[i] = i * weight * 65536;
+        t[256 + i] = i * bias * (1 - weight) / 4 * 65536;
+        t[512 + i] = i * (1 - bias) * (1 - weight) / 4 * 65536;
+        t[768 + i] = (t[256 + i] + t[512 + i] + 1) / 2;
+    }
+    const uint32_t *d_t = static_cast<const uint32_t *>(device_blob(c, t, sizeof(t), st));
+    if (!d_t) return 0;
+    return tcv_antialias_launch(src, spitch, dest, dpitch, d_t, width, height, Bpp, nframes, st) ? 1 : 0;
+}
+
 }  // extern "C"

@@ -1,0 +1,362 @@
+// tcvops.cu -- the element-wise libtcvideo plane operations that surround the aclib path:
+// tcv_clip, tcv_reduce, tcv_flip_v, tcv_flip_h, tcv_gamma_correct, tcv_antialias (libtcvideo/tcvideo.c:184-250,
+// 681-980).  One plane of width x height pixels, Bpp 1 or 3, tightly packed; a batch is `nframes` such planes a fixed
+// pitch apart.  Everything here is data movement or a per-byte table map, so the bound is HBM: each kernel reads and
+// writes every byte once with 16-byte accesses wherever the geometry keeps chunks aligned, and falls back to a
+// byte-granular path (same kernel, warp-uniform branch) where it does not.
+#include "fast_common.cuh"
+
+namespace acgpu {
+namespace {
+
+using namespace fast;
+
+constexpr int kThreads = 256;
+
+inline dim3 grid_for(uint64_t work_items, int nframes, int nwaves = 32)
+{
+    long want = ((long)sm_count() * 8 * waves(nwaves) + nframes - 1) / nframes;
+    const long maxgx = (long)((work_items + kThreads - 1) / kThreads);
+    if (want > maxgx) want = maxgx;
+    if (want < 1) want = 1;
+    return dim3((unsigned)want, (unsigned)nframes);
+}
+
+// 16 bytes from any address: one LDG.128 when aligned, else the aligned 32-bit words that hold them, funnel-shifted.
+// COHERENT: plain loads (the caller's source may alias its destination); otherwise the read-only path.
+template <bool COHERENT>
+__device__ __forceinline__ uint32_t ld32(const uint32_t *q) { return COHERENT ? *q : __ldg(q); }
+template <bool COHERENT>
+__device__ __forceinline__ uint4 ld16_any(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 15) == 0) return COHERENT ? *reinterpret_cast<const uint4 *>(p) : ldg128(p);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t w0 = ld32<COHERENT>(q), w1 = ld32<COHERENT>(q + 1), w2 = ld32<COHERENT>(q + 2), w3 = ld32<COHERENT>(q + 3);
+    const uint32_t w4 = sh ? ld32<COHERENT>(q + 4) : 0u;
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Window copy: destination row y shows bytes [sxb, sxb + cn) of source row y*row_mul + row_add at its bytes
+// [cl, cl + cn) and `fill` everywhere else (and in every row whose source row falls outside the source).
+// Serves tcv_clip (tcvideo.c:184-250: crop and/or grow with black borders) and the rows-only case of tcv_reduce
+// (:706-711).  The destination frame is walked as flat 16-byte chunks; a chunk that lies inside one row's copy span
+// is one (possibly unaligned) 16-byte load and one aligned store.
+
+__device__ __forceinline__ uint32_t window_byte(const TcvWindow &p, const uint8_t *src, uint32_t off)
+{
+    const uint32_t y = off / p.dBpl, xb = off - y * p.dBpl;
+    const int sr = (int)y * p.row_mul + p.row_add;
+    if (sr < 0 || sr >= p.srows || xb < p.cl || xb >= p.cl + p.cn) return p.fill & 0xFFu;
+    return src[(size_t)sr * p.sBpl + p.sxb + (xb - p.cl)];
+}
+
+__global__ void __launch_bounds__(kThreads) k_window(TcvWindow p)
+{
+    const uint8_t *src = p.src + (size_t)blockIdx.y * p.spitch;
+    uint8_t *dst = p.dst + (size_t)blockIdx.y * p.dpitch;
+    const uint32_t N = p.dBpl * (uint32_t)p.drows, nchunks = (N + 15) / 16;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
+        const uint32_t off = c * 16;
+        const bool whole = p.vec && off + 16 <= N;
+        if (whole) {
+            const uint32_t y = off / p.dBpl, xb = off - y * p.dBpl;
+            if (xb + 16 <= p.dBpl) {
+                const int sr = (int)y * p.row_mul + p.row_add;
+                const bool row_ok = sr >= 0 && sr < p.srows;
+                if (!row_ok || xb + 16 <= p.cl || xb >= p.cl + p.cn) {
+                    stg128(dst + off, make_uint4(p.fill, p.fill, p.fill, p.fill));
+                    continue;
+                }
+                if (xb >= p.cl && xb + 16 <= p.cl + p.cn) {
+                    stg128(dst + off, ld16_any<false>(src + (size_t)sr * p.sBpl + p.sxb + (xb - p.cl)));
+                    continue;
+                }
+            }
+            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i >> 2] |= window_byte(p, src, off + i) << (8 * (i & 3));
+            stg128(dst + off, make_uint4(w[0], w[1], w[2], w[3]));
+        } else {
+            for (uint32_t i = 0; i < 16 && off + i < N; i++) dst[off + i] = (uint8_t)window_byte(p, src, off + i);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tcv_reduce, general case (tcvideo.c:694-704): destination pixel (x, y) = source pixel (x*rw, y*rh).
+template <int BPP>
+__global__ void __launch_bounds__(kThreads) k_reduce(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                      uint32_t w, uint32_t ow, uint32_t oh, uint32_t rw, uint32_t rh)
+{
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t n = ow * oh, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t y = i / ow, x = i - y * ow;
+        const uint8_t *s = src + ((size_t)y * rh * w + (size_t)x * rw) * BPP;
+        uint8_t *d = dst + (size_t)i * BPP;
+#pragma unroll
+        for (int k = 0; k < BPP; k++) d[k] = __ldg(s + k);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tcv_flip_v (tcvideo.c:739-766): row y <-> row height-1-y.  Every thread owns one 16-byte column slice of a row PAIR:
+// it reads both slices, then writes both, so src == dest (which the reference allows, :757-762) needs no temporary.
+__global__ void __launch_bounds__(kThreads) k_flip_v(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                      uint32_t Bpl, uint32_t h, int vec)
+{
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t ncr = (Bpl + 15) / 16, n = ((h + 1) / 2) * ncr, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t y = i / ncr, xb = (i - y * ncr) * 16, m = h - 1 - y;
+        const size_t oa = (size_t)y * Bpl + xb, ob = (size_t)m * Bpl + xb;
+        if (vec) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(src + oa), b = *reinterpret_cast<const uint4 *>(src + ob);
+            stg128(dst + oa, b);
+            stg128(dst + ob, a);
+        } else {
+            const uint32_t cnt = min(16u, Bpl - xb);
+            uint8_t a[16], b[16];
+            for (uint32_t k = 0; k < cnt; k++) { a[k] = src[oa + k]; b[k] = src[ob + k]; }
+            for (uint32_t k = 0; k < cnt; k++) { dst[oa + k] = b[k]; dst[ob + k] = a[k]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tcv_flip_h (tcvideo.c:787-818): pixel x <-> pixel width-1-x inside every row; src == dest allowed (:806-814).
+// Vector form (width % 16 == 0): a thread owns one 16-pixel group and its mirror group, reverses the pixel order of
+// both in registers and writes them to each other's place.
+__device__ __forceinline__ uint4 reverse_bytes16(uint4 v)
+{
+    return make_uint4(__byte_perm(v.w, 0, 0x0123), __byte_perm(v.z, 0, 0x0123), __byte_perm(v.y, 0, 0x0123), __byte_perm(v.x, 0, 0x0123));
+}
+// 16 RGB pixels in 12 words -> the same pixels in reverse order
+__device__ __forceinline__ void reverse_pixels48(const uint32_t *w, uint32_t *o)
+{
+    uint32_t px[16];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        px[4 * g + 0] = w[3 * g];
+        px[4 * g + 1] = __byte_perm(w[3 * g], w[3 * g + 1], 0x0543);
+        px[4 * g + 2] = __byte_perm(w[3 * g + 1], w[3 * g + 2], 0x0432);
+        px[4 * g + 3] = w[3 * g + 2] >> 8;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const uint32_t p0 = px[15 - 4 * g], p1 = px[14 - 4 * g], p2 = px[13 - 4 * g], p3 = px[12 - 4 * g];
+        o[3 * g + 0] = __byte_perm(p0, p1, 0x4210);
+        o[3 * g + 1] = __byte_perm(p1, p2, 0x5421);
+        o[3 * g + 2] = __byte_perm(p2, p3, 0x6542);
+    }
+}
+
+template <int BPP>
+__global__ void __launch_bounds__(kThreads) k_flip_h(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                      uint32_t w, uint32_t h, int vec)
+{
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    if (vec) {
+        const uint32_t gpr = w / 16, hg = (gpr + 1) / 2, n = hg * h;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const uint32_t y = i / hg, g = i - y * hg, m = gpr - 1 - g;
+            const size_t row = (size_t)y * w * BPP, oa = row + (size_t)g * 16 * BPP, ob = row + (size_t)m * 16 * BPP;
+            if (BPP == 1) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(src + oa), b = *reinterpret_cast<const uint4 *>(src + ob);
+                stg128(dst + oa, reverse_bytes16(b));
+                stg128(dst + ob, reverse_bytes16(a));
+            } else {
+                uint32_t a[12], b[12], ra[12], rb[12];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const uint4 va = *reinterpret_cast<const uint4 *>(src + oa + 16 * k), vb = *reinterpret_cast<const uint4 *>(src + ob + 16 * k);
+                    a[4 * k] = va.x; a[4 * k + 1] = va.y; a[4 * k + 2] = va.z; a[4 * k + 3] = va.w;
+                    b[4 * k] = vb.x; b[4 * k + 1] = vb.y; b[4 * k + 2] = vb.z; b[4 * k + 3] = vb.w;
+                }
+                reverse_pixels48(a, ra);
+                reverse_pixels48(b, rb);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    stg128(dst + oa + 16 * k, make_uint4(rb[4 * k], rb[4 * k + 1], rb[4 * k + 2], rb[4 * k + 3]));
+                    stg128(dst + ob + 16 * k, make_uint4(ra[4 * k], ra[4 * k + 1], ra[4 * k + 2], ra[4 * k + 3]));
+                }
+            }
+        }
+    } else {
+        const uint32_t hw = (w + 1) / 2, n = hw * h;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const uint32_t y = i / hw, x = i - y * hw, m = w - 1 - x;
+            const size_t row = (size_t)y * w * BPP, oa = row + (size_t)x * BPP, ob = row + (size_t)m * BPP;
+            uint8_t a[BPP], b[BPP];
+#pragma unroll
+            for (int k = 0; k < BPP; k++) { a[k] = src[oa + k]; b[k] = src[ob + k]; }
+#pragma unroll
+            for (int k = 0; k < BPP; k++) { dst[oa + k] = b[k]; dst[ob + k] = a[k]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tcv_gamma_correct (tcvideo.c:840-858): dest[i] = table[src[i]].  The 256-byte table (built on the host with the
+// reference's double arithmetic) sits in shared memory as 64 words: byte lookups conflict at most two-way.
+__global__ void __launch_bounds__(kThreads) k_lut(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                   const uint8_t *table, uint32_t nbytes, int vec)
+{
+    __shared__ uint8_t s_t[256];
+    if (threadIdx.x < 64) reinterpret_cast<uint32_t *>(s_t)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t *>(table) + threadIdx.x);
+    __syncthreads();
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t nchunks = (nbytes + 15) / 16, stride = gridDim.x * blockDim.x;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
+        const uint32_t off = c * 16;
+        if (vec && off + 16 <= nbytes) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + off);
+            const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+            uint32_t out[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t a = s_t[in[k] & 0xFFu], b = s_t[(in[k] >> 8) & 0xFFu], cc = s_t[(in[k] >> 16) & 0xFFu], d = s_t[in[k] >> 24];
+                out[k] = __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(cc, d, 0x0040), 0x5410);
+            }
+            stg128(dst + off, make_uint4(out[0], out[1], out[2], out[3]));
+        } else {
+            for (uint32_t i = off; i < off + 16 && i < nbytes; i++) dst[i] = s_t[src[i]];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tcv_antialias (tcvideo.c:886-980).  Border pixels are copied.  An interior pixel is smoothed when its left (or
+// right) neighbour has the colour of exactly one vertical neighbour and differs from the other one and from the
+// opposite horizontal neighbour ("same colour": every channel differs by < 25, :37,917-927); the smoothed channel is
+// (d[UL] + y[U] + d[UR] + x[L] + c[C] + x[R] + d[DL] + y[D] + d[DR] + 32768) >> 16 in uint32 with the four 16.16 weight
+// tables of :1209-1224 (built on the host in double, like the reference).  tables = c | x | y | d, 256 entries each.
+template <int BPP>
+__device__ __forceinline__ bool aa_same(const uint8_t *p, const uint8_t *q)
+{
+    int worst = 0;
+#pragma unroll
+    for (int k = 0; k < BPP; k++) worst = max(worst, abs((int)__ldg(q + k) - (int)__ldg(p + k)));
+    return worst < 25;
+}
+
+template <int BPP>
+__global__ void __launch_bounds__(kThreads) k_antialias(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                         const uint32_t *tables, uint32_t w, uint32_t h)
+{
+    __shared__ uint32_t s_t[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_t[i] = __ldg(tables + i);
+    __syncthreads();
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t n = w * h, stride = gridDim.x * blockDim.x;
+    const ptrdiff_t Bpl = (ptrdiff_t)w * BPP;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t y = i / w, x = i - y * w;
+        const uint8_t *c = src + (size_t)i * BPP;
+        uint8_t *o = dst + (size_t)i * BPP;
+        bool smooth = false;
+        if (y > 0 && y < h - 1 && x > 0 && x < w - 1) {
+            const uint8_t *l = c - BPP, *r = c + BPP, *u = c - Bpl, *d = c + Bpl;
+            const bool lu = aa_same<BPP>(l, u), ld = aa_same<BPP>(l, d), ru = aa_same<BPP>(r, u), rd = aa_same<BPP>(r, d);
+            if ((lu != ld) || (ru != rd)) smooth = !aa_same<BPP>(l, r);
+        }
+        if (smooth) {
+#pragma unroll
+            for (int k = 0; k < BPP; k++) {
+                const uint8_t *q = c + k;
+                const uint32_t sum = s_t[768 + __ldg(q - Bpl - BPP)] + s_t[512 + __ldg(q - Bpl)] + s_t[768 + __ldg(q - Bpl + BPP)]
+                                   + s_t[256 + __ldg(q - BPP)] + s_t[__ldg(q)] + s_t[256 + __ldg(q + BPP)]
+                                   + s_t[768 + __ldg(q + Bpl - BPP)] + s_t[512 + __ldg(q + Bpl)] + s_t[768 + __ldg(q + Bpl + BPP)]
+                                   + 32768u;
+                o[k] = (uint8_t)(sum >> 16);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < BPP; k++) o[k] = __ldg(c + k);
+        }
+    }
+}
+
+inline bool al16p(const void *p, size_t pitch, int nframes) { return al16(p) && (nframes <= 1 || pitch % 16 == 0); }
+
+}  // namespace
+
+bool tcv_window_launch(TcvWindow p, int nframes, cudaStream_t st)
+{
+    p.vec = al16p(p.dst, p.dpitch, nframes) ? 1 : 0;
+    const uint64_t N = (uint64_t)p.dBpl * p.drows;
+    if (N == 0) return true;
+    k_window<<<grid_for((N + 15) / 16, nframes), kThreads, 0, st>>>(p);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_window");
+    return true;
+}
+
+bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int ow, int oh, int rw, int rh,
+                       int Bpp, int nframes, cudaStream_t st)
+{
+    const uint64_t n = (uint64_t)ow * oh;
+    if (n == 0) return true;
+    const dim3 g = grid_for(n, nframes);
+    if (Bpp == 1) k_reduce<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh);
+    else k_reduce<3><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_reduce");
+    return true;
+}
+
+bool tcv_flip_v_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int h, int Bpp, int nframes, cudaStream_t st)
+{
+    const uint32_t Bpl = (uint32_t)w * Bpp;
+    const int vec = Bpl % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes);
+    const uint64_t n = (uint64_t)((h + 1) / 2) * ((Bpl + 15) / 16);
+    k_flip_v<<<grid_for(n, nframes), kThreads, 0, st>>>(src, spitch, dst, dpitch, Bpl, h, vec);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_flip_v");
+    return true;
+}
+
+bool tcv_flip_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int h, int Bpp, int nframes, cudaStream_t st)
+{
+    const int vec = w % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes);
+    const uint64_t n = vec ? (uint64_t)((w / 16 + 1) / 2) * h : (uint64_t)((w + 1) / 2) * h;
+    const dim3 g = grid_for(n, nframes);
+    if (Bpp == 1) k_flip_h<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, h, vec);
+    else k_flip_h<3><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, h, vec);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_flip_h");
+    return true;
+}
+
+bool tcv_lut_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint8_t *d_table, size_t nbytes,
+                    int nframes, cudaStream_t st)
+{
+    const int vec = al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes);
+    k_lut<<<grid_for((nbytes + 15) / 16, nframes, 8), kThreads, 0, st>>>(src, spitch, dst, dpitch, d_table, (uint32_t)nbytes, vec);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_lut");
+    return true;
+}
+
+bool tcv_antialias_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint32_t *d_tables, int w, int h,
+                          int Bpp, int nframes, cudaStream_t st)
+{
+    const dim3 g = grid_for((uint64_t)w * h, nframes, 8);
+    if (Bpp == 1) k_antialias<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
+    else k_antialias<3><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_antialias");
+    return true;
+}
+
+}  // namespace acgpu
