@@ -53,54 +53,100 @@ __device__ __forceinline__ uint32_t window_byte(const TcvWindow &p, const uint8_
     return src[(size_t)sr * p.sBpl + p.sxb + (xb - p.cl)];
 }
 
+// One destination chunk: classified, fetched (whole chunks only) and returned; the caller stores it.  `kind` tells the
+// caller what to do: 0 = nothing (past the end), 1 = store v, 2 = byte-granular tail / unaligned destination.
+__device__ __forceinline__ int window_chunk(const TcvWindow &p, const uint8_t *src, uint32_t c, uint32_t N, uint4 &v)
+{
+    const uint32_t off = c * 16;
+    if (off >= N) return 0;
+    if (!(p.vec && off + 16 <= N)) return 2;
+    const uint32_t y = off / p.dBpl, xb = off - y * p.dBpl;
+    if (xb + 16 <= p.dBpl) {
+        const int sr = (int)y * p.row_mul + p.row_add;
+        const bool row_ok = sr >= 0 && sr < p.srows;
+        if (!row_ok || xb + 16 <= p.cl || xb >= p.cl + p.cn) {
+            v = make_uint4(p.fill, p.fill, p.fill, p.fill);
+            return 1;
+        }
+        if (xb >= p.cl && xb + 16 <= p.cl + p.cn) {
+            v = ld16_any<false>(src + (size_t)sr * p.sBpl + p.sxb + (xb - p.cl));
+            return 1;
+        }
+    }
+    // mixed chunk (border / row end inside it): walk its 16 bytes with a running (row, column)
+    uint32_t w[4] = {0, 0, 0, 0}, yy = y, xx = xb;
+    int sr = (int)yy * p.row_mul + p.row_add;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint32_t b = p.fill & 0xFFu;
+        if (sr >= 0 && sr < p.srows && xx >= p.cl && xx < p.cl + p.cn) b = __ldg(src + (size_t)sr * p.sBpl + p.sxb + (xx - p.cl));
+        w[i >> 2] |= b << (8 * (i & 3));
+        if (++xx == p.dBpl) { xx = 0; yy++; sr += p.row_mul; }
+    }
+    v = make_uint4(w[0], w[1], w[2], w[3]);
+    return 1;
+}
+
+constexpr int kWinUnroll = 4;     // independent 16-byte loads in flight per thread (a lone load per thread is latency-bound)
+
 __global__ void __launch_bounds__(kThreads) k_window(TcvWindow p)
 {
     const uint8_t *src = p.src + (size_t)blockIdx.y * p.spitch;
     uint8_t *dst = p.dst + (size_t)blockIdx.y * p.dpitch;
     const uint32_t N = p.dBpl * (uint32_t)p.drows, nchunks = (N + 15) / 16;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
-        const uint32_t off = c * 16;
-        const bool whole = p.vec && off + 16 <= N;
-        if (whole) {
-            const uint32_t y = off / p.dBpl, xb = off - y * p.dBpl;
-            if (xb + 16 <= p.dBpl) {
-                const int sr = (int)y * p.row_mul + p.row_add;
-                const bool row_ok = sr >= 0 && sr < p.srows;
-                if (!row_ok || xb + 16 <= p.cl || xb >= p.cl + p.cn) {
-                    stg128(dst + off, make_uint4(p.fill, p.fill, p.fill, p.fill));
-                    continue;
-                }
-                if (xb >= p.cl && xb + 16 <= p.cl + p.cn) {
-                    stg128(dst + off, ld16_any<false>(src + (size_t)sr * p.sBpl + p.sxb + (xb - p.cl)));
-                    continue;
-                }
-            }
-            uint32_t w[4] = {0, 0, 0, 0};
+    const uint32_t per_block = kThreads * kWinUnroll;
+    for (uint32_t base = blockIdx.x * per_block; base < nchunks; base += gridDim.x * per_block) {
+        uint4 v[kWinUnroll];
+        int kind[kWinUnroll];
 #pragma unroll
-            for (int i = 0; i < 16; i++) w[i >> 2] |= window_byte(p, src, off + i) << (8 * (i & 3));
-            stg128(dst + off, make_uint4(w[0], w[1], w[2], w[3]));
-        } else {
-            for (uint32_t i = 0; i < 16 && off + i < N; i++) dst[off + i] = (uint8_t)window_byte(p, src, off + i);
+        for (int k = 0; k < kWinUnroll; k++) kind[k] = window_chunk(p, src, base + k * kThreads + threadIdx.x, N, v[k]);
+#pragma unroll
+        for (int k = 0; k < kWinUnroll; k++) {
+            const uint32_t off = (base + k * kThreads + threadIdx.x) * 16;
+            if (kind[k] == 1) {
+                stg128(dst + off, v[k]);
+            } else if (kind[k] == 2) {
+                for (uint32_t i = 0; i < 16 && off + i < N; i++) dst[off + i] = (uint8_t)window_byte(p, src, off + i);
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // tcv_reduce, general case (tcvideo.c:694-704): destination pixel (x, y) = source pixel (x*rw, y*rh).
+// A thread gathers four consecutive destination pixels (they may wrap to the next destination row) and, when the
+// destination allows it, writes them as whole 32-bit words.
 template <int BPP>
 __global__ void __launch_bounds__(kThreads) k_reduce(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
-                                                      uint32_t w, uint32_t ow, uint32_t oh, uint32_t rw, uint32_t rh)
+                                                      uint32_t w, uint32_t ow, uint32_t oh, uint32_t rw, uint32_t rh, int vec)
 {
     const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
     uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
-    const uint32_t n = ow * oh, stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t y = i / ow, x = i - y * ow;
-        const uint8_t *s = src + ((size_t)y * rh * w + (size_t)x * rw) * BPP;
-        uint8_t *d = dst + (size_t)i * BPP;
+    const uint32_t n = ow * oh, nq = (n + 3) / 4, stride = gridDim.x * blockDim.x;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const uint32_t i0 = q * 4;
+        uint32_t y = i0 / ow, x = i0 - y * ow;
+        uint8_t b[4 * BPP];
 #pragma unroll
-        for (int k = 0; k < BPP; k++) d[k] = __ldg(s + k);
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j < n) {
+                const uint8_t *s = src + ((size_t)y * rh * w + (size_t)x * rw) * BPP;
+#pragma unroll
+                for (int k = 0; k < BPP; k++) b[j * BPP + k] = __ldg(s + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < BPP; k++) b[j * BPP + k] = 0;
+            }
+            if (++x == ow) { x = 0; y++; }
+        }
+        uint8_t *d = dst + (size_t)i0 * BPP;
+        if (vec && i0 + 4 <= n) {
+#pragma unroll
+            for (int k = 0; k < BPP; k++)
+                stg32(d + 4 * k, (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24));
+        } else {
+            for (uint32_t k = 0; k < 4 * BPP && i0 * BPP + k < n * BPP; k++) d[k] = b[k];
+        }
     }
 }
 
@@ -287,6 +333,156 @@ __global__ void __launch_bounds__(kThreads) k_antialias(const uint8_t *src0, siz
     }
 }
 
+// Word-parallel form (width % 4 == 0, 4-byte aligned planes): a thread owns PX = 4*NG horizontally adjacent pixels =
+// W = BPP*NG 32-bit words of an image row.  "Channel differs by >= 25" is evaluated on four bytes at once (|a-b| with
+// VABSDIFF4, then the carry trick ((d & 0x7f) + 103 | d) & 0x80 per byte); the left / right neighbours are the same
+// words funnel-shifted by BPP bytes; for Bpp 3 a pixel's three channel bits are OR-ed onto its first byte with two more
+// funnel shifts; and the smoothing rule is two LOP3s per word on those masks.  No branch depends on the picture until
+// the (usually sparse) pixels that really are smoothed are gathered into a per-warp queue and take the 9-tap table path
+// on full warps.
+//   NG = 4: 16 pixels per thread, 128-bit accesses (width % 16 == 0, 16-byte aligned planes); NG = 1: 32-bit accesses.
+__device__ __forceinline__ uint32_t diff_bits(uint32_t a, uint32_t b)      // bit 7 of each byte: |a - b| >= 25
+{
+    const uint32_t d = __vabsdiffu4(a, b);
+    return (((d & 0x7F7F7F7Fu) + 0x67676767u) | d) & 0x80808080u;
+}
+
+// Per-byte "differs" bits of the thread's W words -> per-PIXEL bits, left on the first byte of every pixel.
+template <int BPP, int W>
+__device__ __forceinline__ void pixel_diff(const uint32_t *a, const uint32_t *b, uint32_t *out)
+{
+    uint32_t m[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) m[k] = diff_bits(a[k], b[k]);
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        if (BPP == 1) {
+            out[k] = m[k];
+        } else {
+            const uint32_t nx = k + 1 < W ? m[k + 1] : 0u;      // a pixel never continues past the thread's last word
+            out[k] = m[k] | __funnelshift_r(m[k], nx, 8) | __funnelshift_r(m[k], nx, 16);
+        }
+    }
+}
+
+template <int BPP, int NG>
+__global__ void __launch_bounds__(kThreads) k_antialias_vec(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                             const uint32_t *tables, uint32_t w, uint32_t h)
+{
+    constexpr int W = BPP * NG, PX = 4 * NG;                // words / pixels per thread
+    __shared__ uint32_t s_t[1024];
+    __shared__ uint32_t s_queue[kThreads / 32][32 * PX];    // per warp: the pixels (y*w + x) that take the 9-tap path
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_t[i] = __ldg(tables + i);
+    __syncthreads();
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t upr = w / PX, wpr = upr * W, n = upr * h, stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t *queue = s_queue[threadIdx.x >> 5];
+    const ptrdiff_t Bpl = (ptrdiff_t)w * BPP;
+    constexpr int SHL = BPP == 1 ? 24 : 8, SHR = BPP == 1 ? 8 : 24;       // funnel shifts that move the row by BPP bytes
+    auto load_words = [](const uint32_t *p, uint32_t *out) {
+        if (NG == 4) {
+#pragma unroll
+            for (int k = 0; k < W / 4; k++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + k);
+                out[4 * k] = v.x; out[4 * k + 1] = v.y; out[4 * k + 2] = v.z; out[4 * k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; k++) out[k] = __ldg(p + k);
+        }
+    };
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {      // warp-uniform trip count
+        const uint32_t i = base + lane;
+        uint32_t S[W], any = 0, y = 0, u = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) S[k] = 0;
+        if (i < n) {
+            y = i / upr;
+            u = i - y * upr;
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(src) + (size_t)y * wpr + (size_t)u * W;
+            uint32_t C[W];
+            load_words(cw, C);
+            if (y > 0 && y < h - 1) {
+                uint32_t U[W], D[W], L[W], R[W], A[W], B[W];
+                load_words(cw - wpr, U);
+                load_words(cw + wpr, D);
+                const uint32_t prev = u > 0 ? __ldg(cw - 1) : 0u, next = u < upr - 1 ? __ldg(cw + W) : 0u;
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    L[k] = __funnelshift_r(k ? C[k - 1] : prev, C[k], SHL);
+                    R[k] = __funnelshift_r(C[k], k + 1 < W ? C[k + 1] : next, SHR);
+                }
+                // smooth = LR differ && ((LU differ) != (LD differ) || (RU differ) != (RD differ))      tcvideo.c:945-949
+                pixel_diff<BPP, W>(L, U, A);
+                pixel_diff<BPP, W>(L, D, B);
+#pragma unroll
+                for (int k = 0; k < W; k++) A[k] ^= B[k];
+                pixel_diff<BPP, W>(R, U, B);
+                pixel_diff<BPP, W>(R, D, S);
+#pragma unroll
+                for (int k = 0; k < W; k++) A[k] |= B[k] ^ S[k];
+                pixel_diff<BPP, W>(L, R, S);
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    // keep the bit on the first byte of each pixel only
+                    constexpr uint32_t kFirst[3] = {0x80000080u, 0x00800000u, 0x00008000u};
+                    S[k] &= A[k] & (BPP == 1 ? 0x80808080u : kFirst[k % 3]);
+                }
+                if (u == 0) S[0] &= ~0x80u;                                                  // x == 0 is copied (:942)
+                if (u == upr - 1) S[W - 1] &= BPP == 1 ? ~0x80000000u : ~0x00008000u;        // so is x == w-1 (:968)
+#pragma unroll
+                for (int k = 0; k < W; k++) any |= S[k];
+            }
+            uint8_t *ow = dst + ((size_t)y * wpr + (size_t)u * W) * 4;
+            if (NG == 4) {
+#pragma unroll
+                for (int k = 0; k < W / 4; k++) stg128(ow + 16 * k, make_uint4(C[4 * k], C[4 * k + 1], C[4 * k + 2], C[4 * k + 3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < W; k++) stg32(ow + 4 * k, C[k]);
+            }
+        }
+        // Smoothed pixels are usually sparse: gather the warp's into a dense queue so the 9-tap work runs on full
+        // warps, then overwrite those pixels (after the copies above; __syncwarp orders the two stores).
+        if (__any_sync(0xFFFFFFFFu, any != 0)) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int k = 0; k < W; k++) mine += __popc(S[k]);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if ((int)lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (mine) {
+                uint32_t slot = incl - mine;
+                const uint32_t px0 = y * w + u * PX;
+#pragma unroll
+                for (int k = 0; k < W; k++)
+                    for (uint32_t f = S[k]; f; f &= f - 1) queue[slot++] = px0 + (uint32_t)(4 * k + ((__ffs(f) - 1) >> 3)) / BPP;
+            }
+            __syncwarp();
+            for (uint32_t r = lane; r < total; r += 32) {
+                const uint32_t px = queue[r];
+                const uint8_t *c = src + (size_t)px * BPP;
+#pragma unroll
+                for (int k = 0; k < BPP; k++) {
+                    const uint8_t *q = c + k;
+                    const uint32_t sum = s_t[768 + __ldg(q - Bpl - BPP)] + s_t[512 + __ldg(q - Bpl)] + s_t[768 + __ldg(q - Bpl + BPP)]
+                                       + s_t[256 + __ldg(q - BPP)] + s_t[__ldg(q)] + s_t[256 + __ldg(q + BPP)]
+                                       + s_t[768 + __ldg(q + Bpl - BPP)] + s_t[512 + __ldg(q + Bpl)] + s_t[768 + __ldg(q + Bpl + BPP)]
+                                       + 32768u;
+                    dst[(size_t)px * BPP + k] = (uint8_t)(sum >> 16);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 inline bool al16p(const void *p, size_t pitch, int nframes) { return al16(p) && (nframes <= 1 || pitch % 16 == 0); }
 
 }  // namespace
@@ -296,7 +492,7 @@ bool tcv_window_launch(TcvWindow p, int nframes, cudaStream_t st)
     p.vec = al16p(p.dst, p.dpitch, nframes) ? 1 : 0;
     const uint64_t N = (uint64_t)p.dBpl * p.drows;
     if (N == 0) return true;
-    k_window<<<grid_for((N + 15) / 16, nframes), kThreads, 0, st>>>(p);
+    k_window<<<grid_for((N + 15) / 16 / kWinUnroll + 1, nframes), kThreads, 0, st>>>(p);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_window");
     return true;
@@ -307,9 +503,10 @@ bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t d
 {
     const uint64_t n = (uint64_t)ow * oh;
     if (n == 0) return true;
-    const dim3 g = grid_for(n, nframes);
-    if (Bpp == 1) k_reduce<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh);
-    else k_reduce<3><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh);
+    const dim3 g = grid_for((n + 3) / 4, nframes);
+    const int vec = ((uintptr_t)dst & 3) == 0 && (nframes <= 1 || dpitch % 4 == 0);
+    if (Bpp == 1) k_reduce<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh, vec);
+    else k_reduce<3><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh, vec);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_reduce");
     return true;
@@ -351,6 +548,19 @@ bool tcv_lut_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpit
 bool tcv_antialias_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint32_t *d_tables, int w, int h,
                           int Bpp, int nframes, cudaStream_t st)
 {
+    const bool vec = w % 4 == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0
+                  && (nframes <= 1 || (spitch % 4 == 0 && dpitch % 4 == 0));
+    if (vec) {
+        const bool wide = w % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes);
+        const dim3 g = grid_for((uint64_t)(w / (wide ? 16 : 4)) * h, nframes, 8);
+        if (wide && Bpp == 1) k_antialias_vec<1, 4><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
+        else if (wide) k_antialias_vec<3, 4><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
+        else if (Bpp == 1) k_antialias_vec<1, 1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
+        else k_antialias_vec<3, 1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
+        note_launch();
+        ACGPU_CHECK_LAUNCH("k_antialias_vec");
+        return true;
+    }
     const dim3 g = grid_for((uint64_t)w * h, nframes, 8);
     if (Bpp == 1) k_antialias<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
     else k_antialias<3><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
