@@ -212,7 +212,8 @@ def test_in_place_packed_and_rgba_permutes(ac, chk):
     """img_yuv_packed.c:22,29,40 and img_rgb_packed.c:22,44: these work with src == dest."""
     w, h = 128, 16
     for sf, df in [(F.IMG_YUY2, F.IMG_UYVY), (F.IMG_YUY2, F.IMG_YVYU), (F.IMG_UYVY, F.IMG_YVYU), (F.IMG_YVYU, F.IMG_UYVY),
-                   (F.IMG_RGBA32, F.IMG_ABGR32), (F.IMG_RGBA32, F.IMG_BGRA32), (F.IMG_ARGB32, F.IMG_RGBA32), (F.IMG_RGBA32, F.IMG_ARGB32)]:
+                   (F.IMG_RGBA32, F.IMG_ABGR32), (F.IMG_RGBA32, F.IMG_BGRA32), (F.IMG_ARGB32, F.IMG_RGBA32), (F.IMG_RGBA32, F.IMG_ARGB32),
+                   (F.IMG_RGB24, F.IMG_BGR24), (F.IMG_BGR24, F.IMG_RGB24)]:    # src/video_trans.c:363-371 (-k) swaps in place
         src = ck.random_frame(sf, w, h, seed=6)
         buf = ac.malloc(src.size).upload(src)
         for tier in (0, 1):
@@ -409,4 +410,26 @@ def test_ragged_420_widths_use_the_vectorised_tier(ac, chk):
                 assert ac.lib.acgpu_last_kernel_tier() == 2, f"{F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h} fell back"
                 for i in range(nf):
                     want = chk.convert(frames[i], sf, df, w, h, prefill=0xA5, pad=0)[1]
+                    assert_same(got[i], want, f"ragged {F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h} frame {i}")
+
+
+def test_ragged_420_widths_yuv_family(ac, chk):
+    """The same ragged widths for 4:2:0 <-> 4:2:2 / 4:4:4 / 4:1:1 / packed / Y8 / GRAY8 / 4:2:0 (Ragged420From / To):
+    luma and the other format stay on aligned flat units, the 4:2:0 chroma rows are reached bytewise; a unit that wraps
+    from an odd row into an even one contributes only its tail to the vertical chroma mean."""
+    others = [F.IMG_YUV422P, F.IMG_YUV444P, F.IMG_YUV411P, F.IMG_YUY2, F.IMG_UYVY, F.IMG_YVYU, F.IMG_Y8, F.IMG_GRAY8,
+              F.IMG_YUV420P, F.IMG_YV12]
+    sizes = [(854, 480, 1), (1080, 40, 2), (766, 32, 1), (40, 8, 3), (50, 16, 2), (18, 16, 2), (24, 2, 1), (426, 240, 1), (20, 4, 2)]
+    for (w, h, nf) in sizes:
+        for o in others:
+            for sf, df in ((F.IMG_YUV420P, o), (o, F.IMG_YUV420P)):
+                frames = np.stack([ck.random_frame(sf, w, h, seed=950 + i) for i in range(nf)])
+                got = ac.convert_batch(frames, sf, df, w, h, prefill=0x5A)
+                # the OTHER format's planes still have to be 16-byte aligned (tiny frames: 4:2:2 V of 24x2 is not)
+                aligned = all(off % 16 == 0 for off in F.plane_offsets(o, w, h)) or o in (F.IMG_YUV420P, F.IMG_YV12)
+                aligned = aligned and (nf == 1 or (F.frame_bytes(sf, w, h) % 16 == 0 and F.frame_bytes(df, w, h) % 16 == 0))
+                if aligned and not (o == F.IMG_YUV411P and w % 4):
+                    assert ac.lib.acgpu_last_kernel_tier() == 2, f"{F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h} fell back"
+                for i in range(nf):
+                    want = chk.convert(frames[i], sf, df, w, h, prefill=0x5A, pad=0)[1]
                     assert_same(got[i], want, f"ragged {F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h} frame {i}")

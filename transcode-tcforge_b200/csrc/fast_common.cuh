@@ -31,6 +31,19 @@ __device__ __forceinline__ uint2 ldg_bytes8(const uint8_t *p, uint32_t nb)
     const uint32_t w0 = __ldg(q), w1 = (4 - s < nb) ? __ldg(q + 1) : 0u, w2 = (8 - s < nb) ? __ldg(q + 2) : 0u;
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
+// nb (1 .. 4*NW) bytes from an address with any alignment into NW words (low bytes first); same word-granular rule.
+template <int NW>
+__device__ __forceinline__ void ldg_bytes(const uint8_t *p, uint32_t nb, uint32_t *out)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t s = (uint32_t)(a & 3), sh = s * 8;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; i++) w[i] = (4u * i < nb + s) ? __ldg(q + i) : 0u;
+#pragma unroll
+    for (int i = 0; i < NW; i++) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
+}
 __device__ __forceinline__ uint64_t u64_of(uint2 v) { return (uint64_t)v.x | ((uint64_t)v.y << 32); }
 __device__ __forceinline__ uint2 uint2_of(uint64_t v) { return make_uint2((uint32_t)v, (uint32_t)(v >> 32)); }
 

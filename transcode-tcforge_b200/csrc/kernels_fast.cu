@@ -12,8 +12,9 @@
 // and the path is HBM-bound (DESIGN.md section 4 has the instruction budget that makes it so).
 //
 // Domain: every plane pointer and frame pitch 16-byte aligned, sizes on the formats' unit grid, and
-// width % 16 == 0 when a 4:2:0 plane is involved (otherwise (width*height) % 16 == 0).  YUV420P <-> RGB also takes
-// any even width >= 16 with (width*height) % 16 == 0 through the ragged-row kernels (S420R / D420R).  Outside it
+// width % 16 == 0 when a 4:2:0 plane is involved (otherwise (width*height) % 16 == 0).  4:2:0 frames of any other even
+// width >= 16 with (width*height) % 16 == 0 go through the ragged-row kernels (S420R / D420R here, Ragged420From / To in
+// kernels_fast_yuv.cu; their chroma planes only need 4-byte alignment).  Outside it
 // convert_fast() returns false and the generic tier runs.
 #include "fast_common.cuh"
 
@@ -740,16 +741,19 @@ static bool fast_domain(const ConvertArgs &a, FastParams *out)
     // byte-aligned accesses anyway (e.g. 50x16: V starts at byte 1000 of the frame)
     const bool ragged_w = any420 && w % 16;
     for (int i = 0; i < 3; i++) {
-        if (a.src.p[i] && !al16(a.src.p[i]) && !(ragged_w && i > 0 && a.srcfmt == IMG_YUV420P)) return false;
-        if (a.dst.p[i] && !al16(a.dst.p[i]) && !(ragged_w && i > 0 && a.dstfmt == IMG_YUV420P)) return false;
+        const bool s_free = ragged_w && i > 0 && a.srcfmt == IMG_YUV420P, d_free = ragged_w && i > 0 && a.dstfmt == IMG_YUV420P;
+        if (a.src.p[i] && (s_free ? ((uintptr_t)a.src.p[i] & 3) != 0 : !al16(a.src.p[i]))) return false;
+        if (a.dst.p[i] && (d_free ? ((uintptr_t)a.dst.p[i] & 3) != 0 : !al16(a.dst.p[i]))) return false;
     }
     bool ragged = false;
     if (any420) {
         if (w % 2 || h % 2) return false;
         if (w % 16) {
-            // ragged 4:2:0 rows: only the YUV420P <-> RGB kernels have a flat-unit form (S420R / D420R)
-            const bool other_rgb = (a.srcfmt == IMG_YUV420P ? dd.kind : sd.kind) == K_RGB && (a.srcfmt == IMG_YUV420P ? dd.bpp : sd.bpp) >= 3;
-            if (!other_rgb || w < 16 || P % 16 || P >= 0x7FFFFFFFu) return false;
+            // ragged 4:2:0 rows: flat-unit kernels (S420R / D420R in this file, Ragged420From / Ragged420To in
+            // kernels_fast_yuv.cu); 4:1:1 needs whole 4-pixel groups per row
+            const int other = a.srcfmt == IMG_YUV420P ? a.dstfmt : a.srcfmt;
+            if (w < 16 || P % 16 || P >= 0x7FFFFFFFu) return false;
+            if (other == IMG_YUV411P && w % 4) return false;
             ragged = true;
         }
     } else {

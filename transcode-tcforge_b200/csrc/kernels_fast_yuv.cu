@@ -387,6 +387,148 @@ struct P420ToPacked {
     }
 };
 
+// ---- ragged 4:2:0 (width % 16 != 0): flat 16-pixel units, byte-aligned chroma rows -----------------------------
+// Rows of such a frame are not 16-byte aligned, so the row-pair kernels above do not apply.  Luma (and every operand
+// of the OTHER format) is still walked as flat, aligned 16-pixel units; only the 4:2:0 chroma planes are reached
+// through byte-aligned accesses.  OTHER: a PlanarKind (P422 / P444 / P411) or 16 + PackedKind.
+template <int OTHER> struct OtherInfo {
+    static constexpr bool packed = OTHER >= 16;
+    static constexpr int q = OTHER - 16;
+    static constexpr int nc = packed ? 8 : chroma_bytes(OTHER);     // chroma bytes per plane per unit-row (planar)
+};
+
+// 4:2:0 -> OTHER: the unit's 8 chroma samples come from gather420 (first part of chroma row y/2, continued on the next
+// row's when the unit wraps); every other row re-reads them (L1/L2 hits), exactly as the C loops do.
+template <int OTHER>
+struct Ragged420From {
+    static constexpr int kMode = MODE_LINEAR, kStage = OtherInfo<OTHER>::packed ? 2 : 0;
+    static __device__ __forceinline__ void run(const FastParams &p, size_t soff, size_t doff, uint32_t u, bool valid,
+                                               uint32_t warp_u0, int nvalid, uint4 *stage, int lane)
+    {
+        using OI = OtherInfo<OTHER>;
+        uint32_t yw[4], uw[2] = {0, 0}, vw[2] = {0, 0};
+        ld4(p.s0 + soff + (size_t)u * 16, valid, yw);
+        if (valid) {
+            const uint32_t w = (uint32_t)p.w, n = u * 16u, y = n / w, x0 = n - y * w;
+            const uint2 uu = gather420(p.s1 + soff, y, x0, w), vv = gather420(p.s2 + soff, y, x0, w);
+            uw[0] = uu.x; uw[1] = uu.y; vw[0] = vv.x; vw[1] = vv.y;
+        }
+        if (OI::packed) {
+            uint32_t o[8];
+            join_packed<OI::q>(yw, uw, vw, o);
+            store_chunks<2>(stage, lane, o, p.d0 + doff + (size_t)warp_u0 * 32, nvalid);
+        } else {
+            st4(p.d0 + doff + (size_t)u * 16, valid, yw);
+            uint32_t d[4];
+            chroma_h<8, OI::nc>(uw, d);
+            stn<OI::nc>(p.d1 + doff + (size_t)u * OI::nc, valid, d);
+            chroma_h<8, OI::nc>(vw, d);
+            stn<OI::nc>(p.d2 + doff + (size_t)u * OI::nc, valid, d);
+        }
+    }
+};
+
+// OTHER -> 4:2:0: luma is a flat copy; chroma row r is made from OTHER's rows 2r and 2r+1, so only the part of a unit
+// that lies on an EVEN row produces samples (one contiguous run: the whole unit, its head, or -- for a unit that
+// wraps from an odd row into an even one -- its tail).  In OTHER's flat layout the sample below is always one row
+// pitch further, wrapped or not.
+template <int OTHER>
+struct Ragged420To {
+    static constexpr int kMode = MODE_LINEAR, kStage = 0;
+    // the run's samples [j0, j0+cnt) of the given plane (planar) / of both planes (packed), vertically combined
+    static __device__ __forceinline__ void combine(const FastParams &p, size_t soff, uint32_t u, uint32_t j0, uint32_t cnt,
+                                                   uint32_t *uo, uint32_t *vo)
+    {
+        using OI = OtherInfo<OTHER>;
+        const uint32_t w = (uint32_t)p.w;
+        if (OI::packed) {                                  // even row copies, odd row (prev+cur+1)/2   img_yuv_mixed.c:144-164
+            uint32_t a[8], b[8], ya[4], ua[2], va[2], ub[2], vb[2];
+            const uint8_t *q = p.s0 + soff + (size_t)u * 32 + 4 * j0;
+            ldg_bytes<8>(q, 4 * cnt, a);
+            ldg_bytes<8>(q + (size_t)w * 2, 4 * cnt, b);
+            split_packed<OI::q>(a, ya, ua, va);
+            split_packed<OI::q>(b, ya, ub, vb);
+            uo[0] = avg_up4(ua[0], ub[0]); uo[1] = avg_up4(ua[1], ub[1]);
+            vo[0] = avg_up4(va[0], vb[0]); vo[1] = avg_up4(va[1], vb[1]);
+            return;
+        }
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const uint8_t *plane = (pl ? p.s2 : p.s1) + soff;
+            uint32_t *o = pl ? vo : uo;
+            if (OTHER == P422) {                           // (a+b+1)/2 vertically                         img_yuv_planar.c:168-181
+                uint32_t a[2], b[2];
+                ldg_bytes<2>(plane + (size_t)u * 8 + j0, cnt, a);
+                ldg_bytes<2>(plane + (size_t)u * 8 + j0 + (w >> 1), cnt, b);
+                o[0] = avg_up4(a[0], b[0]); o[1] = avg_up4(a[1], b[1]);
+            } else if (OTHER == P411) {                    // vertical mean, then replicate x2              :115-131
+                uint32_t a[1], b[1];
+                ldg_bytes<1>(plane + (size_t)u * 4 + (j0 >> 1), cnt >> 1, a);
+                ldg_bytes<1>(plane + (size_t)u * 4 + (j0 >> 1) + (w >> 2), cnt >> 1, b);
+                const uint32_t m = avg_up4(a[0], b[0]);
+                o[0] = __byte_perm(m, 0, 0x1100); o[1] = __byte_perm(m, 0, 0x3322);
+            } else {                                       // 4:4:4: 2x2 box (a+b+c+d+2)/4                   :215-232
+                uint32_t a[4], b[4], r[4];
+                ldg_bytes<4>(plane + (size_t)u * 16 + 2 * j0, 2 * cnt, a);
+                ldg_bytes<4>(plane + (size_t)u * 16 + 2 * j0 + w, 2 * cnt, b);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t sa = (a[i] & 0x00FF00FFu) + ((a[i] >> 8) & 0x00FF00FFu);
+                    const uint32_t sb = (b[i] & 0x00FF00FFu) + ((b[i] >> 8) & 0x00FF00FFu);
+                    r[i] = ((sa + sb + 0x00020002u) >> 2) & 0x00FF00FFu;
+                }
+                o[0] = __byte_perm(r[0], r[1], 0x6420); o[1] = __byte_perm(r[2], r[3], 0x6420);
+            }
+        }
+    }
+    static __device__ __forceinline__ void run(const FastParams &p, size_t soff, size_t doff, uint32_t u, bool valid,
+                                               uint32_t, int, uint4 *, int)
+    {
+        using OI = OtherInfo<OTHER>;
+        uint32_t yw[4];
+        if (OI::packed) {
+            uint32_t a[8], uw[2], vw[2];
+            load_packed16(p.s0 + soff + (size_t)u * 32, valid, a);
+            split_packed<OI::q>(a, yw, uw, vw);
+        } else {
+            ld4(p.s0 + soff + (size_t)u * 16, valid, yw);
+        }
+        st4(p.d0 + doff + (size_t)u * 16, valid, yw);
+        if (!valid) return;
+        const uint32_t w = (uint32_t)p.w, cw = w >> 1, n = u * 16u, y = n / w, x0 = n - y * w;
+        const uint32_t k = min(8u, (w - x0) >> 1);
+        uint32_t ye, j0, cnt, xc;
+        if (!(y & 1)) { ye = y; j0 = 0; cnt = k; xc = x0 >> 1; }
+        else if (k < 8) { ye = y + 1; j0 = k; cnt = 8 - k; xc = 0; }
+        else return;
+        uint32_t uo[2], vo[2];
+        combine(p, soff, u, j0, cnt, uo, vo);
+        const size_t co = (size_t)(ye >> 1) * cw + xc;
+        stg_bytes8(p.d1 + doff + co, make_uint2(uo[0], uo[1]), 0, cnt);
+        stg_bytes8(p.d2 + doff + co, make_uint2(vo[0], vo[1]), 0, cnt);
+    }
+};
+
+bool ragged420_family(const ConvertArgs &a, const FastParams &p)
+{
+    const int nf = a.nframes;
+    cudaStream_t st = a.stream;
+    const bool from = a.srcfmt == IMG_YUV420P;
+    const int other = from ? a.dstfmt : a.srcfmt;
+    switch (other) {
+    case IMG_YUV420P: return launch_op<PlanarLinear<P411, P411>>(p, nf, st, "ragged 420 copy");   // same plane sizes, flat copy
+    case IMG_Y8:      return from ? launch_op<PlanarLinear<P420, PY8>>(p, nf, st, "ragged 420->y8") : launch_op<PlanarLinear<PY8, P420>>(p, nf, st, "ragged y8->420");
+    case IMG_GRAY8:   return from ? launch_op<PlanarLinear<P420, PGRAY>>(p, nf, st, "ragged 420->gray8") : launch_op<PlanarLinear<PGRAY, P420>>(p, nf, st, "ragged gray8->420");
+    case IMG_YUV422P: return from ? launch_op<Ragged420From<P422>>(p, nf, st, "ragged 420->422") : launch_op<Ragged420To<P422>>(p, nf, st, "ragged 422->420");
+    case IMG_YUV444P: return from ? launch_op<Ragged420From<P444>>(p, nf, st, "ragged 420->444") : launch_op<Ragged420To<P444>>(p, nf, st, "ragged 444->420");
+    case IMG_YUV411P: return from ? launch_op<Ragged420From<P411>>(p, nf, st, "ragged 420->411") : launch_op<Ragged420To<P411>>(p, nf, st, "ragged 411->420");
+    case IMG_YUY2:    return from ? launch_op<Ragged420From<16 + QYUY2>>(p, nf, st, "ragged 420->yuy2") : launch_op<Ragged420To<16 + QYUY2>>(p, nf, st, "ragged yuy2->420");
+    case IMG_UYVY:    return from ? launch_op<Ragged420From<16 + QUYVY>>(p, nf, st, "ragged 420->uyvy") : launch_op<Ragged420To<16 + QUYVY>>(p, nf, st, "ragged uyvy->420");
+    case IMG_YVYU:    return from ? launch_op<Ragged420From<16 + QYVYU>>(p, nf, st, "ragged 420->yvyu") : launch_op<Ragged420To<16 + QYVYU>>(p, nf, st, "ragged yvyu->420");
+    default: return false;
+    }
+}
+
 // ---- packed <-> packed: one PRMT per 4-byte group, fully linear (img_yuv_packed.c:30-78) ---------------------
 __global__ void __launch_bounds__(256) k_wordperm(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
                                                  uint32_t sel, uint32_t nchunks)
@@ -488,6 +630,7 @@ bool fast_yuv_family(const ConvertArgs &a, const fast::FastParams &p)
     const int sq = packed_kind(a.srcfmt), dq = packed_kind(a.dstfmt);
     const int nf = a.nframes;
     cudaStream_t st = a.stream;
+    if (p.ragged420) return ragged420_family(a, p);
     if (sp >= 0 && dp >= 0) {
         if (a.srcfmt == IMG_GRAY8 && a.dstfmt == IMG_GRAY8) return launch_op<PlanarLinear<PY8, PY8>>(p, nf, st, "gray8 copy");
         switch (sp) {
