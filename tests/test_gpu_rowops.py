@@ -99,6 +99,10 @@ def test_deinterlace_shapes(ac, tcv, bpp, mode, size):
     (1920, 1080, -80, 0, 8, 8),    # horizontal 1920 -> 1280
     (720, 576, 4, 0, 8, 8),        # horizontal grow
     (64, 32, 0, 3, 8, 2),
+    (1920, 1080, -160, 0, 8, 8),   # horizontal 1920 -> 640: ratio 3, taps too far apart for the window kernel
+    (640, 480, 80, 0, 8, 8),       # horizontal 640 -> 1280
+    (1920, 1080, -1, 0, 8, 8),     # 1920 -> 1912: nearly 1:1, every phase of the weight table
+    (1024, 64, -60, 0, 8, 4),      # 1024 -> 544 (ratio 1.88), scale_h 4
 ])
 def test_resize_shapes(ac, tcv, bpp, case):
     w, h, rw, rh, sw, sh = case
@@ -110,11 +114,18 @@ def test_resize_shapes(ac, tcv, bpp, case):
     src = ac.malloc(nf * sfb + w * bpp).fill(0xEE)
     src.upload(frames.reshape(-1))
     dst = ac.malloc(nf * dfb).fill(0x55)
-    ac._ok(ac.lib.acgpu_resize_batch(src.ptr, dst.ptr, w, h, bpp, rw, rh, sw, sh, sfb, dfb, nf, None))
-    ac.sync()
-    got = dst.download().reshape(nf, dfb)
-    for i in range(nf):
-        assert np.array_equal(got[i], tcv.resize(frames[i], w, h, bpp, rw, rh, sw, sh)), (case, bpp, i)
+    want = [tcv.resize(frames[i], w, h, bpp, rw, rh, sw, sh) for i in range(nf)]
+    for tier in (0, 1):       # 1: the byte-gather horizontal kernel instead of the window kernel
+        dst.fill(0x55)
+        ac.lib.acgpu_force_tier(tier)
+        try:
+            ac._ok(ac.lib.acgpu_resize_batch(src.ptr, dst.ptr, w, h, bpp, rw, rh, sw, sh, sfb, dfb, nf, None))
+        finally:
+            ac.lib.acgpu_force_tier(0)
+        ac.sync()
+        got = dst.download().reshape(nf, dfb)
+        for i in range(nf):
+            assert np.array_equal(got[i], want[i]), (case, bpp, tier, i)
     src.free(); dst.free()
 
 

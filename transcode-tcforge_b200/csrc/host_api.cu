@@ -14,6 +14,8 @@
 #include "acgpu_internal.h"
 
 #include <math.h>
+
+#include <algorithm>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -922,9 +924,32 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
                         off[o] = (uint16_t)so;
                         wgt[o] = wp;
                     }
-            const uint16_t *doff = static_cast<const uint16_t *>(device_blob(c, off.data(), off.size() * sizeof(uint16_t), st));
             const uint32_t *dwgt = static_cast<const uint32_t *>(device_blob(c, wgt.data(), wgt.size() * sizeof(uint32_t), st));
-            if (!doff || !dwgt) return 0;
+            if (!dwgt) return 0;
+            // window form: the four first taps of every output word within 8 source bytes (any ratio up to ~2:1)
+            std::vector<uint32_t> meta(off.size() / 4);
+            bool windowed = tls.force_tier != 1;
+            for (size_t ow = 0; ow < meta.size() && windowed; ow++) {
+                uint32_t lo = off[4 * ow], hi = lo;
+                for (int j = 1; j < 4; j++) { lo = std::min<uint32_t>(lo, off[4 * ow + j]); hi = std::max<uint32_t>(hi, off[4 * ow + j]); }
+                if (hi - lo > 7) { windowed = false; break; }
+                uint32_t sel = 0;
+                for (int j = 0; j < 4; j++) sel |= (off[4 * ow + j] - lo) << (4 * j);
+                meta[ow] = lo | (sel << 16);
+            }
+            if (windowed) {
+                const uint32_t *dmeta = static_cast<const uint32_t *>(device_blob(c, meta.data(), meta.size() * sizeof(uint32_t), st));
+                if (!dmeta) return 0;
+                for (int f0 = 0; f0 < nframes; f0 += 32768) {
+                    const int nf = nframes - f0 < 32768 ? nframes - f0 : 32768;
+                    if (!resize_h_win_launch(src + (size_t)f0 * sp_, sp_, dest + (size_t)f0 * dp_, dp_, dmeta, dwgt, width, new_w,
+                                             new_h, Bpp, nf, st))
+                        return 0;
+                }
+                return 1;
+            }
+            const uint16_t *doff = static_cast<const uint16_t *>(device_blob(c, off.data(), off.size() * sizeof(uint16_t), st));
+            if (!doff) return 0;
             for (int f0 = 0; f0 < nframes; f0 += 32768) {
                 const int nf = nframes - f0 < 32768 ? nframes - f0 : 32768;
                 if (!resize_h_row_launch(src + (size_t)f0 * sp_, sp_, dest + (size_t)f0 * dp_, dp_, doff, dwgt, width, new_w,

@@ -9,6 +9,8 @@
 // every row of every frame of a batch (grid.y = frame); each thread moves one 16-byte chunk when the
 // row geometry is 16-byte aligned, bytes otherwise.
 #include "acgpu_internal.h"
+
+#include <algorithm>
 #include "pixmath.cuh"
 
 #include <string.h>
@@ -230,6 +232,54 @@ __global__ void __launch_bounds__(256) k_resize_h_row(const uint8_t *src, size_t
     }
 }
 
+// Window form of the same kernel (the default whenever the table allows it, i.e. for every ratio up to ~2:1): the four
+// first taps of an output word lie within 8 consecutive source bytes, and the second taps are those bytes + Bpp.  So
+// instead of eight byte gathers the thread reads four aligned shared-memory words at the window base, funnel-shifts them
+// to the base's byte alignment (and by a further Bpp bytes for the second taps), picks the taps with one PRMT each using a
+// host-built selector, interleaves them with two more PRMTs and blends two outputs per word with dp2a.lo / dp2a.hi.
+// meta[ow] = window base (source byte offset in the row, 16 bits) | PRMT selector (16 bits); weights as above.
+template <int BPP>
+__global__ void __launch_bounds__(256) k_resize_h_win(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
+                                                     const uint32_t *__restrict__ meta, const uint32_t *__restrict__ twgt,
+                                                     int src_row_bytes, int dst_row_bytes, int rows)
+{
+    extern __shared__ uint4 s_row[];
+    const int row0 = blockIdx.x * kResizeRows;
+    const int nrows = min(kResizeRows, rows - row0);
+    const uint8_t *s = src + (size_t)blockIdx.y * spitch + (size_t)row0 * src_row_bytes;
+    uint8_t *d = dst + (size_t)blockIdx.y * dpitch + (size_t)row0 * dst_row_bytes;
+    const int schunks = (src_row_bytes >> 4) * nrows;          // the rows are contiguous in the frame
+    for (int c = threadIdx.x; c < schunks; c += blockDim.x) cp_async16(&s_row[c], s + (size_t)c * 16);
+    cp_async_wait_all();
+    __syncthreads();
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_row);
+    const int wpr = dst_row_bytes >> 2, swpr = src_row_bytes >> 2;
+    for (int ow = threadIdx.x; ow < wpr; ow += blockDim.x) {
+        const uint32_t m = __ldg(meta + ow);
+        const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(twgt) + ow);      // four weight pairs
+        const uint32_t base = m & 0xFFFFu, sel = m >> 16, sh = (base & 3u) * 8;
+        const uint32_t *rw = sw + (base >> 2);
+#pragma unroll
+        for (int r = 0; r < kResizeRows; r++) {
+            if (r < nrows) {
+                const uint32_t *q = rw + (size_t)r * swpr;
+                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = BPP == 1 ? 0u : q[3];
+                const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh), W2 = __funnelshift_r(w2, w3, sh);
+                const uint32_t A = __byte_perm(W0, W1, sel);
+                const uint32_t B = __byte_perm(__funnelshift_r(W0, W1, 8 * BPP), __funnelshift_r(W1, W2, 8 * BPP), sel);
+                const uint32_t X0 = __byte_perm(A, B, 0x5140), X1 = __byte_perm(A, B, 0x7362);
+                uint32_t v0, v1, v2, v3;
+                asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(v0) : "r"(w4.x), "r"(X0), "r"(32768u));
+                asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(v1) : "r"(w4.y), "r"(X0), "r"(32768u));
+                asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(v2) : "r"(w4.z), "r"(X1), "r"(32768u));
+                asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(v3) : "r"(w4.w), "r"(X1), "r"(32768u));
+                __stcs(reinterpret_cast<uint32_t *>(d + (size_t)r * dst_row_bytes) + ow,
+                       __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410));
+            }
+        }
+    }
+}
+
 inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
@@ -330,6 +380,25 @@ bool resize_h_row_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t
     k_resize_h_row<<<g, 256, smem, st>>>(src, spitch, dst, dpitch, d_off, d_wgt, srb, drb, Bpp, rows);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_resize_h_row");
+    return true;
+}
+
+bool resize_h_win_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint32_t *d_meta,
+                         const uint32_t *d_wgt, int width, int new_w, int rows, int Bpp, int nframes, cudaStream_t st)
+{
+    const int srb = width * Bpp, drb = new_w * Bpp;
+    if (rows <= 0 || nframes <= 0) return true;
+    const size_t smem = (size_t)srb * kResizeRows + 32;        // the last window may look up to 16 bytes past the rows
+    auto kern = Bpp == 1 ? k_resize_h_win<1> : k_resize_h_win<3>;
+    if (smem > 48 * 1024 && !check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
+        return false;
+    dim3 g((unsigned)((rows + kResizeRows - 1) / kResizeRows), (unsigned)nframes);
+    // block size: the output words of a row split evenly over the passes (320 words: 2 x 160 threads, not 256 + 64)
+    const int wpr = drb / 4, passes = (wpr + 255) / 256;
+    const int threads = std::min(256, (((wpr + passes - 1) / passes) + 31) / 32 * 32);
+    kern<<<g, threads, smem, st>>>(src, spitch, dst, dpitch, d_meta, d_wgt, srb, drb, rows);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_resize_h_win");
     return true;
 }
 
