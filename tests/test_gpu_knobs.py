@@ -1,0 +1,31 @@
+"""-m gpu: every kernel variant that is selectable only through a profiling knob stays bit-exact.
+
+The knobs ($ACGPU_FORCE_RAGGED, $ACGPU_FLAT420, $ACGPU_TMA, $ACGPU_WAVES; DESIGN.md section 4, profiles/r1_experiments.md)
+are read once per process, so each setting runs tests/knob_worker.py in a fresh interpreter."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.mark.parametrize("env,tier", [
+    ({"ACGPU_FORCE_RAGGED": "0"}, 0),      # row-pair kernels for RGB -> 4:2:0 too (the default walks it flat)
+    ({"ACGPU_FORCE_RAGGED": "1"}, 0),      # flat one-row-per-unit kernels for every 4:2:0 pair, aligned widths included
+    ({"ACGPU_FLAT420": "0"}, 0),           # no flat walk for 4:2:0 -> RGB at widths that idle lanes
+    ({"ACGPU_WAVES": "3"}, 0),             # a different grid shape
+    ({"ACGPU_TMA": "0"}, 3),               # tier 3: bulk (TMA) stores
+    ({"ACGPU_TMA": "1"}, 3),               # tier 3: bulk-async staged loads
+    ({"ACGPU_TMA": "2"}, 3),               # tier 3: staged loads + bulk stores
+], ids=lambda v: "-".join(f"{k[6:]}{x}" for k, x in v.items()) if isinstance(v, dict) else f"tier{v}")
+def test_knob_variants_match_the_checker(env, tier):
+    e = dict(os.environ)
+    e.update(env)
+    e["PYTHONPATH"] = os.pathsep.join([ROOT, HERE, e.get("PYTHONPATH", "")])
+    r = subprocess.run([sys.executable, os.path.join(HERE, "knob_worker.py"), str(tier)], capture_output=True, text=True,
+                       env=e, cwd=ROOT, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().startswith("OK"), (env, r.stdout[-400:], r.stderr[-400:])

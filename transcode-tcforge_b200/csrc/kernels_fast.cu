@@ -755,6 +755,14 @@ static bool fast_domain(const ConvertArgs &a, FastParams *out)
             if (w < 16 || P % 16 || P >= 0x7FFFFFFFu) return false;
             if (other == IMG_YUV411P && w % 4) return false;
             ragged = true;
+        } else {
+            // The flat one-row-per-unit walk also serves aligned widths.  RGB -> 4:2:0 prefers it at every size measured
+            // (no idle lanes when width/16 is not a multiple of 32: PAL 0.98 -> 1.07 of peak, 720p 1.03 -> 1.06, 1080p
+            // 1.06 -> 1.07); 4:2:0 -> RGB and the YUV family lose 5-25 % to the repeated chroma work and stay on the
+            // row-pair kernels.  $ACGPU_FORCE_RAGGED = 1 / 0 forces it on / off for every 4:2:0 pair (profiling).
+            static const int force = [] { const char *e = getenv("ACGPU_FORCE_RAGGED"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+            const bool rgb_to_420 = sd.kind == K_RGB && a.dstfmt == IMG_YUV420P;
+            if (P < 0x7FFFFFFFu && (force == 1 || (force == -1 && rgb_to_420))) ragged = true;
         }
     } else {
         if (P % 16) return false;
