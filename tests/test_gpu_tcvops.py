@@ -159,3 +159,18 @@ def test_rejections_match_the_reference(ac):
     assert L.acgpu_antialias_batch(buf.ptr, buf.ptr, 64, 32, 1, 0.5, 0.5, 0, 0, 1, None) == 0          # overlap
     assert b"overlap" in L.acgpu_last_error()
     buf.free()
+
+
+def test_batches_longer_than_one_grid(ac, tcv):
+    """grid.y carries the frame index, so batches above 65535 frames are cut into several launches."""
+    w, h, bpp, nf = 16, 2, 1, 70000
+    frames = ck.splitmix_bytes(nf * w * h * bpp, 77).reshape(nf, -1)
+    _, got = ac.plane_op_batch("flip_v", frames, w * h * bpp, w, h, bpp)
+    assert np.array_equal(got.reshape(nf, h, w), frames.reshape(nf, h, w)[:, ::-1])
+    _, got = ac.plane_op_batch("gamma_correct", frames, w * h * bpp, w, h, bpp, 2.2)
+    table = ck.Oracle().gamma_table(2.2)
+    assert np.array_equal(got, table[frames])
+    _, got = ac.plane_op_batch("clip", frames, (w - 4) * h * bpp, w, h, bpp, 2, 2, 0, 0, 0)
+    assert np.array_equal(got.reshape(nf, h, w - 4), frames.reshape(nf, h, w)[:, :, 2:-2])
+    for i in (0, 32767, 32768, 65535, 65536, nf - 1):
+        assert np.array_equal(ac.plane_op_batch("flip_h", frames[i:i + 1], w * h, w, h, bpp)[1][0], tcv.flip_h(frames[i], w, h, bpp)[1])

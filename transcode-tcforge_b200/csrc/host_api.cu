@@ -193,6 +193,16 @@ std::atomic<int> g_staged_calls{0};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// grid.y carries the frame index (<= 65535): longer batches are cut into launches of 32768 frames
+template <class F>
+int per_frame_chunk(int nframes, F launch)
+{
+    for (int f0 = 0; f0 < nframes; f0 += 32768)
+        if (!launch(f0, nframes - f0 < 32768 ? nframes - f0 : 32768)) return 0;
+    return 1;
+}
+
+
 void plane_sizes(int fmt, int w, int h, size_t out[3], int *np)
 {
     const FmtDesc d = describe(fmt);
@@ -1031,7 +1041,8 @@ int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t pit
     if (!frames || width <= 0 || height <= 0) { set_error("acgpu_decolor_rgb24_batch: invalid frame parameters"); return 0; }
     if (nframes <= 0) return 1;
     cudaStream_t st = pick_stream(c, stream);
-    if (tls.force_tier != 1 && decolor_rgb24_fast(frames, pitch, width, height, nframes, st)) { tls.last_tier = 2; return 1; }
+    if (tls.force_tier != 1 && per_frame_chunk(nframes, [&](int f0, int nf) {
+            return decolor_rgb24_fast(frames + (size_t)f0 * pitch, pitch, width, height, nf, st); })) { tls.last_tier = 2; return 1; }
     // outside the vectorised domain: the reference's own two steps through a temporary gray plane
     const size_t gpitch = align_up((size_t)width * height, 256);
     if (!ensure_arena(c, gpitch * (size_t)nframes)) return 0;
@@ -1079,7 +1090,12 @@ int acgpu_clip_batch(const uint8_t *src, uint8_t *dest, int width, int height, i
     p.cn = (uint32_t)((copy_w > 0 ? copy_w : 0) * Bpp);
     p.sxb = (uint32_t)((clip_left > 0 ? clip_left : 0) * Bpp);
     p.fill = 0x01010101u * black_pixel;
-    return tcv_window_launch(p, nframes, pick_stream(c, stream)) ? 1 : 0;
+    cudaStream_t st = pick_stream(c, stream);
+    return per_frame_chunk(nframes, [&](int f0, int nf) {
+        TcvWindow q = p;
+        q.src += (size_t)f0 * spitch; q.dst += (size_t)f0 * dpitch;
+        return tcv_window_launch(q, nf, st);
+    });
 }
 
 int acgpu_reduce_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, int reduce_w, int reduce_h,
@@ -1092,7 +1108,10 @@ int acgpu_reduce_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     if (nframes <= 0) return 1;
     cudaStream_t st = pick_stream(c, stream);
     if (reduce_w != 1)      // tcvideo.c:694-704
-        return tcv_reduce_launch(src, spitch, dest, dpitch, width, width / reduce_w, height / reduce_h, reduce_w, reduce_h, Bpp, nframes, st) ? 1 : 0;
+        return per_frame_chunk(nframes, [&](int f0, int nf) {
+            return tcv_reduce_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, width, width / reduce_w,
+                                     height / reduce_h, reduce_w, reduce_h, Bpp, nf, st);
+        });
     // :706-715 whole rows: every reduce_h-th one, or (reduce_h == 1) the plain copy
     TcvWindow p{};
     p.src = src; p.spitch = spitch; p.dst = dest; p.dpitch = dpitch;
@@ -1100,7 +1119,11 @@ int acgpu_reduce_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     p.drows = height / reduce_h; p.srows = height;
     p.row_mul = reduce_h; p.row_add = 0;
     p.cl = 0; p.cn = p.dBpl; p.sxb = 0;
-    return tcv_window_launch(p, nframes, st) ? 1 : 0;
+    return per_frame_chunk(nframes, [&](int f0, int nf) {
+        TcvWindow q = p;
+        q.src += (size_t)f0 * spitch; q.dst += (size_t)f0 * dpitch;
+        return tcv_window_launch(q, nf, st);
+    });
 }
 
 int acgpu_flip_v_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, size_t spitch, size_t dpitch,
@@ -1110,7 +1133,10 @@ int acgpu_flip_v_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
-    return tcv_flip_v_launch(src, spitch, dest, dpitch, width, height, Bpp, nframes, pick_stream(c, stream)) ? 1 : 0;
+    cudaStream_t st = pick_stream(c, stream);
+    return per_frame_chunk(nframes, [&](int f0, int nf) {
+        return tcv_flip_v_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, width, height, Bpp, nf, st);
+    });
 }
 
 int acgpu_flip_h_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, size_t spitch, size_t dpitch,
@@ -1120,7 +1146,10 @@ int acgpu_flip_h_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
-    return tcv_flip_h_launch(src, spitch, dest, dpitch, width, height, Bpp, nframes, pick_stream(c, stream)) ? 1 : 0;
+    cudaStream_t st = pick_stream(c, stream);
+    return per_frame_chunk(nframes, [&](int f0, int nf) {
+        return tcv_flip_h_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, width, height, Bpp, nf, st);
+    });
 }
 
 int acgpu_gamma_correct_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double gamma,
@@ -1136,7 +1165,9 @@ int acgpu_gamma_correct_batch(const uint8_t *src, uint8_t *dest, int width, int 
     for (int i = 0; i < 256; i++) table[i] = (uint8_t)(pow((i / 255.0), gamma) * 255);    // tcvideo.c:1180-1189, host doubles
     const uint8_t *d_table = static_cast<const uint8_t *>(device_blob(c, table, sizeof(table), st));
     if (!d_table) return 0;
-    return tcv_lut_launch(src, spitch, dest, dpitch, d_table, (size_t)width * height * Bpp, nframes, st) ? 1 : 0;
+    return per_frame_chunk(nframes, [&](int f0, int nf) {
+        return tcv_lut_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, d_table, (size_t)width * height * Bpp, nf, st);
+    });
 }
 
 int acgpu_antialias_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double weight, double bias,
@@ -1161,7 +1192,9 @@ int acgpu_antialias_batch(const uint8_t *src, uint8_t *dest, int width, int heig
     }
     const uint32_t *d_t = static_cast<const uint32_t *>(device_blob(c, t, sizeof(t), st));
     if (!d_t) return 0;
-    return tcv_antialias_launch(src, spitch, dest, dpitch, d_t, width, height, Bpp, nframes, st) ? 1 : 0;
+    return per_frame_chunk(nframes, [&](int f0, int nf) {
+        return tcv_antialias_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, d_t, width, height, Bpp, nf, st);
+    });
 }
 
 }  // extern "C"
