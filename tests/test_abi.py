@@ -86,6 +86,36 @@ def test_fails_loudly_without_a_device(ac):
     assert ok == 0       # never silently computed on the CPU
 
 
+def test_frame_entry_points_reject_what_libtcvideo_rejects(ac):
+    """Host logic, no device needed: the parameter checks of tcv_clip / tcv_reduce / tcv_flip_* / tcv_gamma_correct /
+    tcv_antialias / tcv_deinterlace / tcv_resize (libtcvideo/tcvideo.c:192-202, 291-311, 436-457, 690-699, 848-851,
+    899-903) run before anything touches the GPU, return 0 and say why."""
+    L = ac.lib
+    p = 0x1000          # never dereferenced: every call below is rejected by its argument checks
+
+    def why():
+        return L.acgpu_last_error().decode()
+
+    assert L.acgpu_clip_batch(p, p, 64, 32, 2, 0, 0, 0, 0, 0, 0, 0, 1, None) == 0 and "invalid frame parameters" in why()
+    assert L.acgpu_clip_batch(p, p, 64, 32, 1, 40, 24, 0, 0, 0, 0, 0, 1, None) == 0 and "clipping parameters" in why()
+    assert L.acgpu_clip_batch(p, p, 64, 32, 3, 0, 0, 33, -1, 0, 0, 0, 1, None) == 0 and "clipping parameters" in why()
+    assert L.acgpu_clip_batch(None, p, 64, 32, 1, 0, 0, 0, 0, 0, 0, 0, 1, None) == 0 and "invalid frame parameters" in why()
+    assert L.acgpu_reduce_batch(p, p, 64, 32, 1, 0, 1, 0, 0, 1, None) == 0 and "reduction parameters" in why()
+    assert L.acgpu_reduce_batch(p, p, 64, 32, 1, 2, -3, 0, 0, 1, None) == 0 and "reduction parameters" in why()
+    assert L.acgpu_flip_v_batch(p, p, 0, 32, 1, 0, 0, 1, None) == 0 and "invalid frame parameters" in why()
+    assert L.acgpu_flip_h_batch(p, None, 64, 32, 3, 0, 0, 1, None) == 0 and "invalid frame parameters" in why()
+    assert L.acgpu_gamma_correct_batch(p, p, 64, 32, 1, 0.0, 0, 0, 1, None) == 0 and "invalid gamma" in why()
+    assert L.acgpu_gamma_correct_batch(p, p, 64, 32, 1, float("nan"), 0, 0, 1, None) == 0 and "invalid gamma" in why()
+    assert L.acgpu_antialias_batch(p, p + 4096, 64, 32, 1, 1.01, 0.5, 0, 0, 1, None) == 0 and "antialiasing parameters" in why()
+    assert L.acgpu_antialias_batch(p, p + 4096, 64, 32, 1, 0.5, -0.01, 0, 0, 1, None) == 0 and "antialiasing parameters" in why()
+    assert L.acgpu_antialias_batch(p, p, 64, 32, 1, 0.5, 0.5, 0, 0, 1, None) == 0 and "overlap" in why()
+    assert L.acgpu_deinterlace_batch(p, p, 64, 32, 1, 7, 0, 0, 1, None) == 0 and "invalid mode" in why()
+    assert L.acgpu_deinterlace_batch(p, p, 64, 32, 4, 0, 0, 0, 1, None) == 0 and "invalid frame parameters" in why()
+    assert L.acgpu_resize_batch(p, p, 64, 32, 1, 0, -1, 3, 8, 0, 0, 1, None) == 0 and "scale" in why()
+    assert L.acgpu_resize_batch(p, p, 60, 32, 1, 0, -1, 8, 8, 0, 0, 1, None) == 0 and "divide" in why()
+    assert L.acgpu_resize_batch(p, p, 64, 32, 1, -8, 0, 8, 8, 0, 0, 1, None) == 0 and "not positive" in why()
+
+
 def test_product_never_touches_the_oracle():
     """The product path must not import, link or load anything under oracle/."""
     for dirpath, _, files in os.walk(entry.PKG_DIR):
