@@ -104,6 +104,13 @@ __device__ __forceinline__ uint32_t channel_word(uint32_t yword, uint32_t ysel, 
     const int jc = BIAS ? __viaddmin_s32_relu(j, -BIAS, pixmath::kJMax) : __vimin_s32_relu(j, pixmath::kJMax);
     return (uint32_t)jc * pixmath::kJMul + pixmath::kJAdd;
 }
+// the last two steps of channel_word on a ready j
+template <int BIAS>
+__device__ __forceinline__ uint32_t clamp_scale(int j)
+{
+    const int jc = BIAS ? __viaddmin_s32_relu(j, -BIAS, pixmath::kJMax) : __vimin_s32_relu(j, pixmath::kJMax);
+    return (uint32_t)jc * pixmath::kJMul + pixmath::kJAdd;
+}
 // (a.b3, b.b3, c.b3, d.b3) -> one word
 __device__ __forceinline__ uint32_t pack_top4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {

@@ -105,9 +105,21 @@ __device__ __forceinline__ void convert_row(const uint32_t *yw, const int *cr, c
                 word = yw[g];
                 sel = 0x10u << (8 * k);
             }
-            xa[k] = channel_word<kBiasRB>(word, sel, SWAP ? cb[s] : cr[s]);
-            xg[k] = channel_word<kBiasG>(word, sel, cg[s]);
-            xc[k] = channel_word<kBiasRB>(word, sel, SWAP ? cr[s] : cb[s]);
+            if (ACGPU_LUT16 && SI::nchroma == 16) {
+                // 4:4:4: every pixel has its own chroma sample, so unpacking the table words (5 instructions per sample)
+                // costs more than feeding them to dp2a as they are: cr[s] / cb[s] hold the packed V / U table words
+                // (low half: R or B term, high half: G term), Y16 = 16*Y is shared by the three channels.
+                const uint32_t y16 = __dp4a(word, sel, 0u), tv = (uint32_t)cr[s], tu = (uint32_t)cb[s];
+                const uint32_t jr = dp2a_lo_uu(tv, 0x0001u, y16), jb = dp2a_lo_uu(tu, 0x0001u, y16);
+                const uint32_t jg = dp2a_lo_uu(tu, 0x0100u, dp2a_lo_uu(tv, 0x0100u, y16));
+                xa[k] = clamp_scale<kBiasRB>((int)(SWAP ? jb : jr));
+                xg[k] = clamp_scale<kBiasG>((int)jg);
+                xc[k] = clamp_scale<kBiasRB>((int)(SWAP ? jr : jb));
+            } else {
+                xa[k] = channel_word<kBiasRB>(word, sel, SWAP ? cb[s] : cr[s]);
+                xg[k] = channel_word<kBiasG>(word, sel, cg[s]);
+                xc[k] = channel_word<kBiasRB>(word, sel, SWAP ? cr[s] : cb[s]);
+            }
         }
         if (BPP == 3) {
             out[g * 3 + 0] = pack_top4(xa[0], xg[0], xc[0], xa[1]);
@@ -174,6 +186,7 @@ __device__ __forceinline__ void chroma_terms(const int2 *tab, uint32_t U, uint32
 #if ACGPU_LUT16
     const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tab);
     const uint32_t tv = t32[V], tu = t32[256 + U];
+    if (SRC == S444) { cr = (int)tv; cb = (int)tu; cg = 0; return; }      // consumed packed, see convert_row
     cr = (int)(tv & 0xFFFFu);
     cb = (int)(tu & 0xFFFFu);
     cg = (int)((tv >> 16) + (tu >> 16));
