@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--tier", type=int, default=0)
+    ap.add_argument("--content", default="random", choices=["random", "smooth"],
+                    help="random: uniform bytes (worst case for the chroma-table bank conflicts); smooth: a soft gradient "
+                         "with +-2 noise, closer to a natural picture (neighbouring lanes hit the same table words)")
     args = ap.parse_args()
     w, h = map(int, args.size.split("x"))
     if args.pairs == "cfg2":
@@ -52,7 +55,11 @@ def main():
         ab = F.algorithmic_bytes(sf, df, w, h)
         batch = max(8, int(1.5e9 // ab))
         src, dst = ac.malloc(batch * sfb), ac.malloc(batch * dfb)
-        host = rng.integers(0, 256, size=sfb, dtype=np.uint8)
+        if args.content == "random":
+            host = rng.integers(0, 256, size=sfb, dtype=np.uint8)
+        else:
+            i = np.arange(sfb, dtype=np.int64)
+            host = ((i // 61) % 200 + 28 + rng.integers(-2, 3, size=sfb)).astype(np.uint8)
         for i in range(batch):
             lib.acgpu_memcpy_h2d(src.ptr + i * sfb, host.ctypes.data, sfb, None)
         ac.sync()
