@@ -16,6 +16,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", default="1920x1080")
 ap.add_argument("--frames", type=int, default=128)
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--only", default="", help="run only the lines whose label contains this text (for ncu captures)")
+ap.add_argument("--bpp", type=int, default=0, help="1 or 3 (default: both)")
 a = ap.parse_args()
 w, h = map(int, a.size.split("x"))
 pkg = e.load_package(); ac = pkg.AcGpu(); assert ac.ac_init(pkg.AC_CUDA) == 1
@@ -33,6 +35,8 @@ def blocky(w, h, bpp):
 
 
 def run(name, fn, n, in_b, out_b):
+    if a.only and a.only not in name:
+        return
     for _ in range(3):
         assert fn() == 1, lib.acgpu_last_error()
     lib.acgpu_event_record(e0, st)
@@ -44,7 +48,7 @@ def run(name, fn, n, in_b, out_b):
     print("%-34s %9.0f frames/s %8.1f GB/s  %.3f" % (name, n / ms * 1e3, gbs, gbs / peak), flush=True)
 
 
-for bpp in (1, 3):
+for bpp in ((a.bpp,) if a.bpp else (1, 3)):
     n = max(a.frames // bpp, 1)
     fb = w * h * bpp
     src = ac.malloc(n * fb); dst = ac.malloc(n * (w + 64) * (h + 16) * bpp)
