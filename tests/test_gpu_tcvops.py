@@ -47,13 +47,13 @@ def out_bytes(op, w, h, bpp, args):
     return w * h * bpp
 
 
-def gpu_case(ac, case, nframes=1, gap=0):
+def gpu_case(ac, case, nframes=1, gap=0, src_gap=0):
     key, op, (w, h, bpp), args, kind, seed = case
     frames = np.stack([tcv_cases.image(kind, w, h, bpp, seed + 1000 * i) for i in range(nframes)])
     inplace = op in ("flip_v", "flip_h") and args[0]
     call_args = () if op in ("flip_v", "flip_h") else args
     ok, got = ac.plane_op_batch(OPS.get(op, op), frames, out_bytes(op, w, h, bpp, args), w, h, bpp, *call_args,
-                                inplace=inplace, dst_gap=gap)
+                                inplace=inplace, dst_gap=gap, src_gap=src_gap)
     return ok, got, frames
 
 
@@ -76,13 +76,13 @@ def test_case_list_matches_reference_digests_through_libacgpu(ac):
 
 
 def test_case_list_batched_with_gaps_against_the_checker(ac, tcv):
-    """Three frames per launch with a 48-byte gap between destination planes: frames are independent and the gap
-    stays untouched."""
+    """Three frames per launch with a 48-byte gap between destination planes and a 16- or 7-byte gap between source
+    planes (the latter knocks the batch off the 16-byte-aligned paths): frames are independent, the gaps stay untouched."""
     for case in tcv_cases.cases():
         key, op, (w, h, bpp), args, kind, seed = case
         if op in ("deinterlace", "resize") or (op in ("flip_v", "flip_h") and args[0]):
             continue
-        ok, got, frames = gpu_case(ac, case, nframes=3, gap=48)
+        ok, got, frames = gpu_case(ac, case, nframes=3, gap=48, src_gap=(16 if (seed & 1) else 7))
         n_out = out_bytes(op, w, h, bpp, args)
         for i in range(3):
             c2 = (key, op, (w, h, bpp), args, kind, seed + 1000 * i)

@@ -247,19 +247,22 @@ class AcGpu:
                                                w, h, nframes, stream)
 
     def plane_op_batch(self, op: str, frames: np.ndarray, out_bytes: int, w: int, h: int, bpp: int, *args,
-                       prefill: int = 0x55, inplace: bool = False, dst_gap: int = 0):
+                       prefill: int = 0x55, inplace: bool = False, dst_gap: int = 0, src_gap: int = 0):
         """Upload [nframes, w*h*bpp] planes, run ``acgpu_<op>_batch`` (clip / reduce / flip_v / flip_h / gamma_correct /
         antialias / deinterlace / resize) once over the batch, download [nframes, out_bytes + dst_gap].
         Returns ``(ok, planes)``; ``inplace`` passes the source buffer as destination."""
         nf, sfb = frames.shape[0], w * h * bpp
         fn = getattr(self.lib, f"acgpu_{op}_batch")
-        ds = self.malloc(nf * sfb).upload(np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1))
+        sp = sfb + src_gap
+        hs = np.full((nf, sp), 0xEE, dtype=np.uint8)
+        hs[:, :sfb] = np.ascontiguousarray(frames, dtype=np.uint8).reshape(nf, sfb)
+        ds = self.malloc(nf * sp).upload(hs.reshape(-1))
         if inplace:
-            dd, dp = ds, sfb
+            dd, dp = ds, sp
         else:
             dp = out_bytes + dst_gap
             dd = self.malloc(max(nf * dp, 1)).fill(prefill)
-        ok = fn(ds.ptr, dd.ptr, w, h, bpp, *args, sfb, dp, nf, None)
+        ok = fn(ds.ptr, dd.ptr, w, h, bpp, *args, sp, dp, nf, None)
         self.sync()
         out = dd.download(nf * dp).reshape(nf, dp) if ok else None
         ds.free()
