@@ -36,6 +36,22 @@ template <int NW>
 __device__ __forceinline__ void ldg_bytes(const uint8_t *p, uint32_t nb, uint32_t *out)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if (NW % 4 == 0 && nb == 4u * NW && (a & 15) == 0) {          // whole and aligned after all (uniform along a row)
+#pragma unroll
+        for (int i = 0; i < NW / 4; i++) {
+            const uint4 v = ldg128(p + 16 * i);
+            out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+        }
+        return;
+    }
+    if (NW % 2 == 0 && nb == 4u * NW && (a & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < NW / 2; i++) {
+            const uint2 v = ldg64(p + 8 * i);
+            out[2 * i] = v.x; out[2 * i + 1] = v.y;
+        }
+        return;
+    }
     const uint32_t s = (uint32_t)(a & 3), sh = s * 8;
     const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
     uint32_t w[NW + 1];
