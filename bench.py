@@ -51,6 +51,17 @@ METRIC = {
 }
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -217,7 +228,7 @@ def run_reference(args, kind, a, b, w, h, name):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": name, "width": w, "height": h, "path": "aclib stock path ac_init(AC_ALL) => SSE2 asm" if accel else "aclib C path",
                    "threads": cores, "step": f"{per_step:.1f} s of frame-parallel conversion on all host cores"},
-        "cpu_baseline": {"value": round(v, 2), "unit": "frames/s", "cores": cores, "kind": kd,
+        "cpu_baseline": {"value": round(v, 2), "unit": "frames/s", "cores": cores, "kind": kd, "cpu_model": cpu_model(),
                          "sample": f"{args.steps} x {per_step:.1f} s, {cores} pthreads, each cycling through 4 distinct frames"},
         "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -417,7 +428,7 @@ def main():
             "sample": f"5 s per variant on {cores} pthreads + 2.5 s on 1 thread, same frame size, each thread cycling through 4 distinct frames",
             "path": "aclib stock ac_init(AC_ALL) => SSE2",
             "c_path_all_cores": round(res[("c", cores)], 2), "sse2_1_thread": round(res[("stock", 1)], 2),
-            "c_path_1_thread": round(res[("c", 1)], 2),
+            "c_path_1_thread": round(res[("c", 1)], 2), "cpu_model": cpu_model(),
         }
     print(json.dumps(line), flush=True)
     dc.close()
