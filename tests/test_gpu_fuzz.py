@@ -1,0 +1,107 @@
+"""-m gpu: seeded differential fuzzing of acgpu_imgconvert_batch against the checker.
+
+Random format pairs, sizes on the unit grid (small, odd-ish, ragged 4:2:0 widths, vector-friendly), 1-3 frames per
+launch, planes placed at random offsets inside each frame slab (aligned for about half of the cases, so both the
+vectorised and the generic tier are exercised) with canary-filled gaps between planes and frames.  Every destination
+byte is compared -- the converted planes with the checker's output, everything else with the canary."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+import checkers as ck
+
+pkg = entry.load_package()
+F = pkg.F
+pytestmark = pytest.mark.gpu
+
+CANARY = 0xC3
+
+
+@pytest.fixture(scope="module")
+def ac():
+    a = pkg.AcGpu()
+    assert a.ac_init(pkg.AC_ALL) == 1, a.last_error()
+    return a
+
+
+@pytest.fixture(scope="module")
+def chk():
+    return ck.best_checker()
+
+
+def layout(rng, sizes, aligned):
+    """Plane offsets inside a frame slab and the frame pitch."""
+    offs, o = [], 0
+    for s in sizes:
+        o += int(rng.integers(0, 4)) * 16 if aligned else int(rng.integers(0, 40))
+        offs.append(o)
+        o += s
+    pitch = o + (int(rng.integers(0, 4)) * 16 if aligned else int(rng.integers(0, 40)))
+    if aligned:
+        pitch = (pitch + 15) // 16 * 16
+    return offs, max(pitch, 1)
+
+
+def pick_size(rng, sf, df, aligned):
+    uw, uh = F.size_unit(sf, df)
+    kind = int(rng.integers(0, 4))
+    if kind == 0:                                   # small
+        w, h = int(rng.integers(1, 24)) * uw, int(rng.integers(1, 12)) * uh
+    elif kind == 1:                                 # wide and flat (long rows, several warps per row)
+        w, h = int(rng.integers(30, 520)) * uw, int(rng.integers(1, 4)) * uh
+    elif kind == 2:                                 # sixteen-pixel grid
+        w, h = int(rng.integers(1, 40)) * 16, int(rng.integers(1, 10)) * 2 * uh
+    else:                                           # ragged: even width, width*height a multiple of 16
+        w = int(rng.integers(9, 120)) * 2 * max(uw // 2, 1)
+        h = int(rng.integers(1, 6)) * 8
+    w -= w % uw
+    h -= h % uh
+    return max(w, uw), max(h, uh)
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_fuzz_batched_conversions(ac, chk, chunk):
+    rng = np.random.default_rng(9000 + chunk)
+    fmts = F.FORMATS_15
+    tiers = {1: 0, 2: 0}
+    for case in range(60):
+        sf, df = fmts[int(rng.integers(0, len(fmts)))], fmts[int(rng.integers(0, len(fmts)))]
+        aligned = bool(rng.integers(0, 2))
+        w, h = pick_size(rng, sf, df, aligned)
+        nf = int(rng.integers(1, 4))
+        ssz, dsz = F.plane_sizes(sf, w, h), F.plane_sizes(df, w, h)
+        soff, spitch = layout(rng, ssz, aligned)
+        doff, dpitch = layout(rng, dsz, aligned)
+        frames = [ck.random_frame(sf, w, h, seed=int(rng.integers(0, 1 << 30))) for _ in range(nf)]
+        hs = np.full(nf * spitch + 64, 0x11, np.uint8)
+        for f in range(nf):
+            o = 0
+            for p, s in enumerate(ssz):
+                hs[f * spitch + soff[p]: f * spitch + soff[p] + s] = frames[f][o:o + s]
+                o += s
+        dsrc = ac.malloc(hs.size).upload(hs)
+        ddst = ac.malloc(nf * dpitch + 64).fill(CANARY)
+        sp = (C.c_void_p * 3)(*[dsrc.ptr + soff[p] if p < len(ssz) else None for p in range(3)])
+        dp = (C.c_void_p * 3)(*[ddst.ptr + doff[p] if p < len(dsz) else None for p in range(3)])
+        ok = ac.lib.acgpu_imgconvert_batch(sp, sf, spitch, dp, df, dpitch, w, h, nf, None)
+        ac.sync()
+        what = f"chunk {chunk} case {case}: {F.NAMES[sf]}->{F.NAMES[df]} {w}x{h} nf={nf} aligned={aligned} tier={ac.lib.acgpu_last_kernel_tier()}"
+        assert ok == 1, (what, ac.last_error())
+        tiers[ac.lib.acgpu_last_kernel_tier()] += 1
+        got = ddst.download()
+        want = np.full_like(got, CANARY)
+        for f in range(nf):
+            _, d = chk.convert(frames[f], sf, df, w, h, prefill=CANARY, pad=0)
+            o = 0
+            for p, s in enumerate(dsz):
+                want[f * dpitch + doff[p]: f * dpitch + doff[p] + s] = d[o:o + s]
+                o += s
+        if not np.array_equal(got, want):
+            bad = np.flatnonzero(got != want)
+            raise AssertionError(f"{what}: {bad.size} bytes differ, first at {bad[0]} (got {got[bad[0]]}, want {want[bad[0]]})")
+        assert np.array_equal(dsrc.download(), hs), what + ": source modified"
+        dsrc.free()
+        ddst.free()
+    assert tiers[1] >= 10 and tiers[2] >= 10, tiers      # the mix must keep exercising both tiers
