@@ -433,3 +433,37 @@ def test_ragged_420_widths_yuv_family(ac, chk):
                 for i in range(nf):
                     want = chk.convert(frames[i], sf, df, w, h, prefill=0x5A, pad=0)[1]
                     assert_same(got[i], want, f"ragged {F.NAMES[sf]}->{F.NAMES[df]} @ {w}x{h} frame {i}")
+
+
+def test_legacy_call_with_every_mix_of_pointer_kinds(ac, chk):
+    """ac_imgconvert(src planes, ..., dest planes, ...) with the source and the destination independently in pageable
+    host memory, page-locked host memory (acgpu_host_alloc) or device memory: libacgpu classifies the pointers per call
+    (host planes are staged, device planes are used in place), the bytes are the same in all nine combinations."""
+    import ctypes as C
+
+    def place(kind, data):
+        if kind == "pageable":
+            arr = np.array(data, dtype=np.uint8, copy=True)
+            return arr, arr.ctypes.data, (lambda: arr.copy()), (lambda: None)
+        if kind == "pinned":
+            pb = ac.pinned(data.size)
+            pb.array[:] = data
+            return pb, pb.ptr, (lambda: pb.array.copy()), pb.free
+        db = ac.malloc(data.size).upload(data)
+        return db, db.ptr, db.download, db.free
+
+    for (w, h) in [(64, 16), (50, 16), (30, 6)]:
+        for sf, df in [(F.IMG_YUV420P, F.IMG_RGB24), (F.IMG_BGRA32, F.IMG_YUV422P), (F.IMG_UYVY, F.IMG_YUV444P), (F.IMG_YUV420P, F.IMG_ARGB32)]:
+            src = ck.random_frame(sf, w, h, seed=31)
+            want = chk.convert(src, sf, df, w, h, prefill=0x6B, pad=0)[1]
+            so, do = F.plane_offsets(sf, w, h), F.plane_offsets(df, w, h)
+            for sk in ("pageable", "pinned", "device"):
+                for dk in ("pageable", "pinned", "device"):
+                    _s, sptr, _sread, sfree = place(sk, src)
+                    _d, dptr, dread, dfree = place(dk, np.full(want.size, 0x6B, np.uint8))
+                    sp = (C.c_void_p * 3)(*[sptr + o for o in so] + [None] * (3 - len(so)))
+                    dp = (C.c_void_p * 3)(*[dptr + o for o in do] + [None] * (3 - len(do)))
+                    assert ac.lib.ac_imgconvert(sp, sf, dp, df, w, h) == 1, (sk, dk, ac.last_error())
+                    ac.sync()
+                    assert_same(dread(), want, f"{F.NAMES[sf]}->{F.NAMES[df]} {w}x{h} src {sk} dest {dk}")
+                    sfree(); dfree()
