@@ -153,3 +153,23 @@ def test_deinterlace_drop_field(ac, mode, first):
             assert np.array_equal(got[i, : h // 2], want)
             assert (got[i, h // 2:] == 0x55).all()
         src.free(); dst.free()
+
+
+def test_table_cache_eviction_never_frees_a_table_in_use(ac, tcv):
+    """libacgpu caches the small device tables it builds (resize weights / window selectors, gamma and antialias
+    tables, row-operation lists) per thread, 64 entries, least recently used.  A call that needs two tables must not
+    lose the first one when the second one's miss evicts old entries: run well past the cache size with calls that
+    need one table and calls that need two, checking every result."""
+    w, h, bpp = 256, 8, 1
+    src = ck.splitmix_bytes(w * h * bpp, 123)
+    f = src[None, :]
+    for i in range(150):
+        g = 0.5 + i * 0.01                                    # one new table per call
+        ok, got = ac.plane_op_batch("gamma_correct", f, w * h * bpp, w, h, bpp, g)
+        assert ok == 1 and np.array_equal(got[0], tcv.gamma(src, w, h, bpp, g)[1]), ("gamma", i)
+        rw = -(i % 11) - 1                                    # 256 -> 248 ... 168: two new tables per distinct width
+        width = w - 8 * (i % 3)                               # 256, 248, 240 wide sources: 33 distinct table pairs
+        s2 = src[: width * h]
+        nw = width + rw * 8
+        ok, got = ac.plane_op_batch("resize", s2[None, :], nw * h * bpp, width, h, bpp, rw, 0, 8, 8)
+        assert ok == 1 and np.array_equal(got[0], tcv.resize(s2, width, h, bpp, rw, 0, 8, 8)), ("resize", i, width, nw)

@@ -357,16 +357,27 @@ uint64_t fnv1a(const void *p, size_t n)
 }
 
 // Returns a device copy of a small host table, cached per (thread, device) by content.
+constexpr size_t kBlobCacheEntries = 64;
 void *device_blob(DevCtx *c, const void *host, size_t bytes, cudaStream_t st)
 {
+    // The list is kept in least-recently-used order: a hit moves to the back, a full cache drops its OLDER HALF.  One API
+    // call asks for a handful of tables at most, so a table handed out earlier in the same call (hit or miss) is never
+    // among the ones freed by a later miss of that call.
     const uint64_t h = fnv1a(host, bytes);
-    for (const Blob &b : c->blobs)
-        if (b.hash == h && b.host.size() == bytes && memcmp(b.host.data(), host, bytes) == 0) return b.dptr;
-    if (c->blobs.size() >= 64) {
+    for (size_t i = 0; i < c->blobs.size(); i++) {
+        Blob &b = c->blobs[i];
+        if (b.hash == h && b.host.size() == bytes && memcmp(b.host.data(), host, bytes) == 0) {
+            void *d = b.dptr;
+            if (i + 1 != c->blobs.size()) std::rotate(c->blobs.begin() + (ptrdiff_t)i, c->blobs.begin() + (ptrdiff_t)i + 1, c->blobs.end());
+            return d;
+        }
+    }
+    if (c->blobs.size() >= kBlobCacheEntries) {
         cudaStreamSynchronize(c->stream);
-        cudaDeviceSynchronize();
-        for (const Blob &b : c->blobs) cudaFree(b.dptr);
-        c->blobs.clear();
+        cudaDeviceSynchronize();          // kernels on caller-supplied streams may still be reading the old tables
+        const size_t drop = c->blobs.size() / 2;
+        for (size_t i = 0; i < drop; i++) cudaFree(c->blobs[i].dptr);
+        c->blobs.erase(c->blobs.begin(), c->blobs.begin() + (ptrdiff_t)drop);
     }
     void *d = nullptr;
     if (!check(cudaMalloc(&d, bytes ? bytes : 16), "cudaMalloc(table)")) return nullptr;
