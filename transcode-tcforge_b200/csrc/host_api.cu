@@ -66,7 +66,7 @@ struct ThreadCtx {
             DevCtx &c = dev[d];
             if (!c.stream && !c.arena && !c.bounce && c.blobs.empty() && !c.pipe_stream[0]) continue;
             if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
-            if (c.stream) cudaStreamSynchronize(c.stream);
+            cudaDeviceSynchronize();     // batched calls may have run on caller-supplied streams that still read our tables
             for (int s = 0; s < kPipeSlots; s++) {
                 if (c.pipe_stream[s]) { cudaStreamSynchronize(c.pipe_stream[s]); cudaStreamDestroy(c.pipe_stream[s]); }
                 if (c.pipe_buf[s]) cudaFree(c.pipe_buf[s]);
