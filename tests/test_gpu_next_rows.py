@@ -107,3 +107,36 @@ def test_frames_host_pipeline(ac, chk, case):
     ac._ok(ac.lib.acgpu_imgconvert_frames_host(src.ctypes.data, sf, dst.ctypes.data, df, w, h, nf))
     assert np.array_equal(dst, np.asarray(hd.array))
     hs.free(); hd.free()
+
+
+def test_in_place_converts_on_two_streams_share_the_temporary_safely(ac, chk):
+    """src == dest goes through one per-thread temporary (tcvideo.c:1044-1064 allocates its own).  Two such calls on
+    DIFFERENT caller streams, back to back without a sync, must not overlap on that temporary: the second waits for
+    the first (event), both results are right."""
+    w, h, nf = 1920, 1080, 24
+    s1, s2 = ac.lib.acgpu_stream_create(), ac.lib.acgpu_stream_create()
+    jobs = []
+    for k, (sf, df) in enumerate([(F.IMG_RGB24, F.IMG_YUV420P), (F.IMG_RGB24, F.IMG_YUV422P)]):
+        sfb = F.frame_bytes(sf, w, h)
+        one = ck.random_frame(sf, w, h, seed=500 + k)
+        buf = ac.malloc(nf * sfb)
+        for i in range(nf):
+            buf.upload(one, offset=i * sfb)
+        jobs.append((sf, df, sfb, one, buf))
+    for rep in range(3):
+        for (sf, df, sfb, one, buf), st in zip(jobs, (s1, s2)):
+            for i in range(nf):
+                buf.upload(one, offset=i * sfb)
+        ac.sync()
+        for (sf, df, sfb, one, buf), st in zip(jobs, (s1, s2)):
+            ac._ok(ac.lib.acgpu_convert_batch(buf.ptr, buf.ptr, w, h, sf, df, sfb, sfb, nf, st))
+        ac.sync(s1); ac.sync(s2)
+        for (sf, df, sfb, one, buf) in jobs:
+            dfb = F.frame_bytes(df, w, h)
+            want = chk.convert(one, sf, df, w, h, pad=0)[1]
+            got = buf.download().reshape(nf, sfb)
+            for i in range(nf):
+                assert np.array_equal(got[i, :dfb], want), (rep, F.NAMES[df], i)
+    for (_, _, _, _, buf) in jobs:
+        buf.free()
+    ac.lib.acgpu_stream_destroy(s1); ac.lib.acgpu_stream_destroy(s2)

@@ -42,6 +42,7 @@ struct DevCtx {
     cudaEvent_t sleep_ev = nullptr;      // blocking-sync event: how a legacy call waits when many threads are converting
     uint8_t *arena = nullptr;            // device staging for the legacy host-pointer calls
     size_t   arena_cap = 0;
+    cudaEvent_t arena_ev = nullptr;      // recorded after the last asynchronous use of the arena (see arena_acquire)
     uint8_t *bounce = nullptr;           // pinned host mirror of the arena (pageable caller buffers go through it)
     size_t   bounce_cap = 0;
     std::vector<Blob> blobs;
@@ -75,6 +76,7 @@ struct ThreadCtx {
             if (c.arena) cudaFree(c.arena);
             if (c.bounce) cudaFreeHost(c.bounce);
             if (c.sleep_ev) cudaEventDestroy(c.sleep_ev);
+            if (c.arena_ev) cudaEventDestroy(c.arena_ev);
             if (c.stream) cudaStreamDestroy(c.stream);
             cudaGetLastError();
         }
@@ -155,6 +157,20 @@ bool ensure_arena(DevCtx *c, size_t bytes)
     if (!check(cudaMalloc(&c->arena, cap), "cudaMalloc(staging arena)")) return false;
     c->arena_cap = cap;
     return true;
+}
+
+// The arena is one buffer per (thread, device) but the batched entry points run on whatever stream the caller names.
+// A use of the arena on stream B must not start before an earlier, still unfinished use on stream A is over:
+// arena_acquire makes B wait for the event the previous user recorded, arena_release records it.
+bool arena_acquire(DevCtx *c, cudaStream_t st)
+{
+    if (!c->arena_ev) return true;
+    return check(cudaStreamWaitEvent(st, c->arena_ev, 0), "arena wait");
+}
+bool arena_release(DevCtx *c, cudaStream_t st)
+{
+    if (!c->arena_ev && !check(cudaEventCreateWithFlags(&c->arena_ev, cudaEventDisableTiming), "cudaEventCreate")) return false;
+    return check(cudaEventRecord(c->arena_ev, st), "arena record");
 }
 
 bool ensure_bounce(DevCtx *c, size_t bytes)
@@ -293,7 +309,7 @@ bool convert_one(Image si, int sfmt, Image di, int dfmt, int w, int h)
         for (int p = 0; p < snp; p++) { soff[p] = need; need += align_up(ssz[p] + 16, 256); }
     if (dst_host)
         for (int p = 0; p < dnp; p++) { doff[p] = need; need += align_up(dsz[p] + 16, 256); }
-    if (need && !ensure_arena(c, need)) return false;
+    if (need && (!ensure_arena(c, need) || !arena_acquire(c, c->stream))) return false;
 
     ConvertArgs a{};
     a.srcfmt = sfmt; a.dstfmt = dfmt; a.w = w; a.h = h; a.nframes = 1; a.stream = c->stream;
@@ -576,7 +592,7 @@ static void blend_legacy(const uint8_t *src1, const uint8_t *src2, uint8_t *dest
     if (!c) fatal(who);
     const bool h1 = classify(src1) != PK_DEVICE, h2 = classify(src2) != PK_DEVICE, hd = classify(dest) != PK_DEVICE;
     const size_t slot = align_up((size_t)bytes, 256);
-    if ((h1 || h2 || hd) && !ensure_arena(c, 3 * slot)) fatal(who);
+    if ((h1 || h2 || hd) && (!ensure_arena(c, 3 * slot) || !arena_acquire(c, c->stream))) fatal(who);
     const uint8_t *d1 = src1, *d2 = src2;
     uint8_t *dd = dest;
     bool ok = true;
@@ -1032,7 +1048,7 @@ int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, Imag
     size_t rpitch = dpitch;
     if (src == dest) {                    // in place: convert into a temporary, then copy back (tcvideo.c:1044-1064)
         rpitch = align_up(dfb, 256);
-        if (!ensure_arena(c, rpitch * (size_t)nframes)) return 0;
+        if (!ensure_arena(c, rpitch * (size_t)nframes) || !arena_acquire(c, st)) return 0;
         real = c->arena;
     }
     uint8_t *sp[3], *dp[3];
@@ -1041,7 +1057,7 @@ int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, Imag
     if (!acgpu_imgconvert_batch(sp, srcfmt, spitch, dp, destfmt, rpitch, width, height, nframes, stream)) return 0;
     if (src == dest)
         return check(cudaMemcpy2DAsync(dest, dpitch ? dpitch : dfb, real, rpitch, dfb, nframes, cudaMemcpyDeviceToDevice, st),
-                     "acgpu_convert_batch copy back") ? 1 : 0;
+                     "acgpu_convert_batch copy back") && arena_release(c, st) ? 1 : 0;
     return 1;
 }
 
@@ -1056,10 +1072,11 @@ int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t pit
             return decolor_rgb24_fast(frames + (size_t)f0 * pitch, pitch, width, height, nf, st); })) { tls.last_tier = 2; return 1; }
     // outside the vectorised domain: the reference's own two steps through a temporary gray plane
     const size_t gpitch = align_up((size_t)width * height, 256);
-    if (!ensure_arena(c, gpitch * (size_t)nframes)) return 0;
+    if (!ensure_arena(c, gpitch * (size_t)nframes) || !arena_acquire(c, st)) return 0;
     uint8_t *rgb[3] = {frames, nullptr, nullptr}, *gray[3] = {c->arena, nullptr, nullptr};
     return acgpu_imgconvert_batch(rgb, IMG_RGB24, pitch, gray, IMG_GRAY8, gpitch, width, height, nframes, stream)
-        && acgpu_imgconvert_batch(gray, IMG_GRAY8, gpitch, rgb, IMG_RGB24, pitch, width, height, nframes, stream);
+        && acgpu_imgconvert_batch(gray, IMG_GRAY8, gpitch, rgb, IMG_RGB24, pitch, width, height, nframes, stream)
+        && arena_release(c, st);
 }
 
 // ---- the remaining element-wise libtcvideo operations ------------------------------------
