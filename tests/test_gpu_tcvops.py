@@ -174,3 +174,57 @@ def test_batches_longer_than_one_grid(ac, tcv):
     assert np.array_equal(got.reshape(nf, h, w - 4), frames.reshape(nf, h, w)[:, :, 2:-2])
     for i in (0, 32767, 32768, 65535, 65536, nf - 1):
         assert np.array_equal(ac.plane_op_batch("flip_h", frames[i:i + 1], w * h, w, h, bpp)[1][0], tcv.flip_h(frames[i], w, h, bpp)[1])
+
+
+def test_concurrent_threads_each_with_their_own_tables(ac):
+    """transcode runs N frame threads (src/frame_threads.c:174-228); libacgpu keeps streams, staging and the table
+    cache per caller thread.  Six threads mix every frame-granular operation on their own planes; each result is
+    checked against that thread's own reference handle."""
+    import threading
+
+    errors = []
+
+    def worker(tid):
+        try:
+            a = pkg.AcGpu()
+            ref = ck.best_tcv_checker()
+            rng = np.random.default_rng(700 + tid)
+            w, h = 64 + 16 * tid, 24 + 2 * tid
+            for it in range(40):
+                bpp = 1 if (it + tid) % 2 else 3
+                src = tcv_cases.blocky_image(w, h, bpp, 800 + tid * 100 + it)
+                f = src[None, :]
+                op = int(rng.integers(0, 7))
+                if op == 0:
+                    g = 0.4 + 0.05 * int(rng.integers(0, 40))
+                    got, want = a.plane_op_batch("gamma_correct", f, src.size, w, h, bpp, g)[1][0], ref.gamma(src, w, h, bpp, g)[1]
+                elif op == 1:
+                    rw = -int(rng.integers(1, 4))
+                    nw = w + rw * 8
+                    got, want = a.plane_op_batch("resize", f, nw * h * bpp, w, h, bpp, rw, 0, 8, 2)[1][0], ref.resize(src, w, h, bpp, rw, 0, 8, 2)
+                elif op == 2:
+                    rh = int(rng.integers(1, 3))
+                    nh = h + rh * 2
+                    got, want = a.plane_op_batch("resize", f, w * nh * bpp, w, h, bpp, 0, rh, 8, 2)[1][0], ref.resize(src, w, h, bpp, 0, rh, 8, 2)
+                elif op == 3:
+                    args = (int(rng.integers(-3, 6)), int(rng.integers(-3, 6)), int(rng.integers(-2, 4)), int(rng.integers(-2, 4)))
+                    ok_r, want = ref.clip(src, w, h, bpp, *args, black=16)
+                    got = a.plane_op_batch("clip", f, want.size, w, h, bpp, *args, 16)[1][0]
+                elif op == 4:
+                    got, want = a.plane_op_batch("antialias", f, src.size, w, h, bpp, 0.333, 0.5)[1][0], ref.antialias(src, w, h, bpp, 0.333, 0.5)[1]
+                elif op == 5:
+                    mode = int(rng.integers(0, 4))
+                    want = ref.deinterlace(src, w, h, bpp, mode)
+                    got = a.plane_op_batch("deinterlace", f, want.size, w, h, bpp, mode)[1][0]
+                else:
+                    got, want = a.plane_op_batch("flip_h", f, src.size, w, h, bpp)[1][0], ref.flip_h(src, w, h, bpp)[1]
+                if not np.array_equal(got[: want.size], want):
+                    errors.append((tid, it, op))
+                    return
+        except Exception as e:      # noqa: BLE001 -- report through the main thread
+            errors.append((tid, repr(e), a.last_error()))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
