@@ -1,0 +1,88 @@
+// host_ctx.h -- host-side state shared by libacgpu's two host translation units (not installed):
+// host_api.cu (aclib entry points, device/memory helpers, batched conversion, row operations) and
+// host_tcv.cu (the frame-granular libtcvideo entry points).  Everything mutable is per caller thread: callers are N
+// concurrent frame threads (src/frame_threads.c:174-228).
+#pragma once
+
+#include "acgpu_internal.h"
+
+#include <vector>
+
+namespace acgpu {
+
+constexpr int kMaxDev = 16;
+constexpr int kPipeSlots = 3;
+
+struct Blob {               // small device-resident tables cached by content (row-op lists, weights)
+    uint64_t hash;
+    std::vector<uint8_t> host;   // the content itself: a hash match alone is not trusted
+    void    *dptr;
+};
+
+struct DevCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t sleep_ev = nullptr;      // blocking-sync event: how a legacy call waits when many threads are converting
+    uint8_t *arena = nullptr;            // device staging for the legacy host-pointer calls
+    size_t   arena_cap = 0;
+    cudaEvent_t arena_ev = nullptr;      // recorded after the last asynchronous use of the arena (see arena_acquire)
+    uint8_t *bounce = nullptr;           // pinned host mirror of the arena (pageable caller buffers go through it)
+    size_t   bounce_cap = 0;
+    std::vector<Blob> blobs;
+    cudaStream_t pipe_stream[kPipeSlots] = {nullptr, nullptr, nullptr};
+    uint8_t *pipe_buf[kPipeSlots] = {nullptr, nullptr, nullptr};
+    size_t   pipe_cap[kPipeSlots] = {0, 0, 0};
+};
+
+struct ThreadCtx {
+    int      device = -1;
+    DevCtx   dev[kMaxDev];
+    char     err[512] = {0};
+    uint64_t launches = 0;
+    int      last_tier = 0;
+    int      force_tier = 0;
+
+    // A caller thread that exits gives its stream, staging buffers and cached tables back.  Best effort: at process
+    // exit the CUDA runtime may already be gone, in which case these calls fail harmlessly.
+    ~ThreadCtx()
+    {
+        for (int d = 0; d < kMaxDev; d++) {
+            DevCtx &c = dev[d];
+            if (!c.stream && !c.arena && !c.bounce && c.blobs.empty() && !c.pipe_stream[0]) continue;
+            if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+            cudaDeviceSynchronize();     // batched calls may have run on caller-supplied streams that still read our tables
+            for (int s = 0; s < kPipeSlots; s++) {
+                if (c.pipe_stream[s]) { cudaStreamSynchronize(c.pipe_stream[s]); cudaStreamDestroy(c.pipe_stream[s]); }
+                if (c.pipe_buf[s]) cudaFree(c.pipe_buf[s]);
+            }
+            for (Blob &b : c.blobs) cudaFree(b.dptr);
+            if (c.arena) cudaFree(c.arena);
+            if (c.bounce) cudaFreeHost(c.bounce);
+            if (c.sleep_ev) cudaEventDestroy(c.sleep_ev);
+            if (c.arena_ev) cudaEventDestroy(c.arena_ev);
+            if (c.stream) cudaStreamDestroy(c.stream);
+            cudaGetLastError();
+        }
+    }
+};
+
+extern thread_local ThreadCtx tls;
+
+DevCtx      *ctx();                                            // binds the thread's device, creates its stream on first use
+cudaStream_t pick_stream(DevCtx *c, acgpu_stream_t s);         // the caller's stream, or the thread's own
+bool  ensure_arena(DevCtx *c, size_t bytes);
+bool  arena_acquire(DevCtx *c, cudaStream_t st);               // orders uses of the arena on different streams
+bool  arena_release(DevCtx *c, cudaStream_t st);
+void *device_blob(DevCtx *c, const void *host, size_t bytes, cudaStream_t st);   // cached device copy of a small host table
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// grid.y carries the frame index (<= 65535): longer batches are cut into launches of 32768 frames
+template <class F>
+int per_frame_chunk(int nframes, F launch)
+{
+    for (int f0 = 0; f0 < nframes; f0 += 32768)
+        if (!launch(f0, nframes - f0 < 32768 ? nframes - f0 : 32768)) return 0;
+    return 1;
+}
+
+}  // namespace acgpu
