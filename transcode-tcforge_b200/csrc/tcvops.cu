@@ -150,6 +150,40 @@ __global__ void __launch_bounds__(kThreads) k_reduce(const uint8_t *src0, size_t
     }
 }
 
+// reduce_w == 2 (the usual "half size" preview), width % 32 == 0, aligned planes: a thread turns 32 source pixels
+// (two or six 128-bit loads) into 16 destination pixels (one or three 128-bit stores) by keeping the even ones.
+template <int BPP>
+__global__ void __launch_bounds__(kThreads) k_reduce_w2(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                         uint32_t w, uint32_t oh, uint32_t rh)
+{
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t upr = w / 32, n = upr * oh, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t y = i / upr, u = i - y * upr;
+        const uint8_t *s = src + ((size_t)y * rh * w + (size_t)u * 32) * BPP;
+        uint8_t *d = dst + ((size_t)y * (w / 2) + (size_t)u * 16) * BPP;
+        if (BPP == 1) {
+            const uint4 a = ldg128(s), b = ldg128(s + 16);
+            stg128(d, make_uint4(__byte_perm(a.x, a.y, 0x6420), __byte_perm(a.z, a.w, 0x6420),
+                                 __byte_perm(b.x, b.y, 0x6420), __byte_perm(b.z, b.w, 0x6420)));
+        } else {
+            uint32_t px[32], o[12];
+            load_rgb16<L_RGB24>(s, 0, true, px);
+            load_rgb16<L_RGB24>(s + 48, 0, true, px + 16);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {       // four kept pixels (source 8g, 8g+2, 8g+4, 8g+6) -> three words
+                const uint32_t p0 = px[8 * g], p1 = px[8 * g + 2], p2 = px[8 * g + 4], p3 = px[8 * g + 6];
+                o[3 * g + 0] = __byte_perm(p0, p1, 0x4210);
+                o[3 * g + 1] = __byte_perm(p1, p2, 0x5421);
+                o[3 * g + 2] = __byte_perm(p2, p3, 0x6542);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) stg128(d + 16 * k, make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // tcv_flip_v (tcvideo.c:739-766): row y <-> row height-1-y.  Every thread owns one 16-byte column slice of a row PAIR:
 // it reads both slices, then writes both, so src == dest (which the reference allows, :757-762) needs no temporary.
@@ -503,6 +537,14 @@ bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t d
 {
     const uint64_t n = (uint64_t)ow * oh;
     if (n == 0) return true;
+    if (rw == 2 && w % 32 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes)) {
+        const dim3 g2 = grid_for((uint64_t)(w / 32) * oh, nframes);
+        if (Bpp == 1) k_reduce_w2<1><<<g2, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, oh, rh);
+        else k_reduce_w2<3><<<g2, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, oh, rh);
+        note_launch();
+        ACGPU_CHECK_LAUNCH("k_reduce_w2");
+        return true;
+    }
     const dim3 g = grid_for((n + 3) / 4, nframes);
     const int vec = ((uintptr_t)dst & 3) == 0 && (nframes <= 1 || dpitch % 4 == 0);
     if (Bpp == 1) k_reduce<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh, vec);
