@@ -105,3 +105,75 @@ def test_fuzz_batched_conversions(ac, chk, chunk):
         dsrc.free()
         ddst.free()
     assert tiers[1] >= 10 and tiers[2] >= 10, tiers      # the mix must keep exercising both tiers
+
+
+# ---- the frame-granular libtcvideo operations ----------------------------------------------------------------------
+import tcv_cases  # noqa: E402
+
+
+def _tcv_call(ac, rng, op, w, h, bpp):
+    """Returns (lib function name, argument tuple after (src, dest, w, h, bpp), checker thunk, output bytes)."""
+    if op == "clip":
+        a = tuple(int(x) for x in (rng.integers(-9, w // 2 + 2), rng.integers(-9, w // 2 + 2), rng.integers(-5, h // 2 + 2), rng.integers(-5, h // 2 + 2)))
+        black = int(rng.integers(0, 256))
+        nw, nh = w - a[0] - a[1], h - a[2] - a[3]
+        return "clip", a + (black,), (lambda t, s: t.clip(s, w, h, bpp, *a, black=black, prefill=CANARY)), max(nw, 0) * max(nh, 0) * bpp
+    if op == "reduce":
+        rw, rh = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        n = w * h * bpp if (rw == 1 and rh == 1) else w * (h // rh) * bpp if rw == 1 else (w // rw) * (h // rh) * bpp
+        return "reduce", (rw, rh), (lambda t, s: t.reduce(s, w, h, bpp, rw, rh, prefill=CANARY)), n
+    if op == "flip_v":
+        return "flip_v", (), (lambda t, s: t.flip_v(s, w, h, bpp)), w * h * bpp
+    if op == "flip_h":
+        return "flip_h", (), (lambda t, s: t.flip_h(s, w, h, bpp)), w * h * bpp
+    if op == "gamma":
+        g = 0.2 + 0.1 * int(rng.integers(0, 30))
+        return "gamma_correct", (g,), (lambda t, s: t.gamma(s, w, h, bpp, g)), w * h * bpp
+    wt, bs = 0.05 * int(rng.integers(0, 21)), 0.05 * int(rng.integers(0, 21))
+    return "antialias", (wt, bs), (lambda t, s: t.antialias(s, w, h, bpp, wt, bs)), w * h * bpp
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_fuzz_plane_operations(ac, chunk):
+    tcv = ck.best_tcv_checker()
+    rng = np.random.default_rng(7700 + chunk)
+    ops = ["clip", "reduce", "flip_v", "flip_h", "gamma", "antialias"]
+    for case in range(70):
+        op = ops[int(rng.integers(0, len(ops)))]
+        bpp = 1 if rng.integers(0, 2) else 3
+        aligned = bool(rng.integers(0, 2))
+        w = int(rng.integers(1, 20)) * 16 if aligned else int(rng.integers(1, 300))
+        h = int(rng.integers(1, 40))
+        nf = int(rng.integers(1, 4))
+        name, args, ref, nout = _tcv_call(ac, rng, op, w, h, bpp)
+        sfb = w * h * bpp
+        s_off, d_off = (0, 0) if aligned else (int(rng.integers(0, 16)), int(rng.integers(0, 16)))
+        spitch = sfb + (int(rng.integers(0, 3)) * 16 if aligned else int(rng.integers(0, 30)))
+        dpitch = nout + (int(rng.integers(0, 3)) * 16 if aligned else int(rng.integers(0, 30)))
+        if aligned:
+            spitch, dpitch = (spitch + 15) // 16 * 16, (dpitch + 15) // 16 * 16
+        frames = [tcv_cases.image("blocky" if op == "antialias" and rng.integers(0, 2) else "random", w, h, bpp, int(rng.integers(0, 1 << 30)))
+                  for _ in range(nf)]
+        hs = np.full(s_off + nf * spitch + 64, 0x22, np.uint8)
+        for f in range(nf):
+            hs[s_off + f * spitch: s_off + f * spitch + sfb] = frames[f]
+        dsrc = ac.malloc(hs.size).upload(hs)
+        ddst = ac.malloc(d_off + nf * dpitch + 64).fill(CANARY)
+        fn = getattr(ac.lib, f"acgpu_{name}_batch")
+        ok = fn(dsrc.ptr + s_off, ddst.ptr + d_off, w, h, bpp, *args, spitch, dpitch, nf, None)
+        ac.sync()
+        what = f"chunk {chunk} case {case}: {name}{args} {w}x{h}x{bpp} nf={nf} aligned={aligned}"
+        got = ddst.download()
+        want = np.full_like(got, CANARY)
+        ok_ref = 1
+        for f in range(nf):
+            ok_ref, d = ref(tcv, frames[f])
+            if ok_ref:
+                want[d_off + f * dpitch: d_off + f * dpitch + nout] = d[:nout]
+        assert ok == ok_ref, (what, ac.last_error())
+        if ok and not np.array_equal(got, want):
+            bad = np.flatnonzero(got != want)
+            raise AssertionError(f"{what}: {bad.size} bytes differ, first at {bad[0]} (got {got[bad[0]]}, want {want[bad[0]]})")
+        assert np.array_equal(dsrc.download(), hs), what + ": source modified"
+        dsrc.free()
+        ddst.free()
