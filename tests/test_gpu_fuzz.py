@@ -129,6 +129,21 @@ def _tcv_call(ac, rng, op, w, h, bpp):
     if op == "gamma":
         g = 0.2 + 0.1 * int(rng.integers(0, 30))
         return "gamma_correct", (g,), (lambda t, s: t.gamma(s, w, h, bpp, g)), w * h * bpp
+    if op == "deinterlace":
+        mode = int(rng.integers(0, 4))
+        if mode == 1 and h < 2:
+            mode = 0
+        return "deinterlace", (mode,), (lambda t, s: (1, t.deinterlace(s, w, h, bpp, mode))), w * (h // 2 if mode >= 2 else h) * bpp
+    if op == "resize":
+        horizontal = bool(rng.integers(0, 2))
+        scales = [sc for sc in (1, 2, 4, 8) if (w if horizontal else h) % sc == 0]
+        sc = scales[int(rng.integers(0, len(scales)))]
+        size = w if horizontal else h
+        lo = -(size // sc) + 1
+        r = int(rng.integers(max(lo, -12), 13)) or 1
+        a = (r, 0, sc, 1) if horizontal else (0, r, 1, sc)
+        nw, nh = w + a[0] * a[2], h + a[1] * a[3]
+        return "resize", a, (lambda t, s: (1, t.resize(s, w, h, bpp, *a))), nw * nh * bpp
     wt, bs = 0.05 * int(rng.integers(0, 21)), 0.05 * int(rng.integers(0, 21))
     return "antialias", (wt, bs), (lambda t, s: t.antialias(s, w, h, bpp, wt, bs)), w * h * bpp
 
@@ -137,7 +152,7 @@ def _tcv_call(ac, rng, op, w, h, bpp):
 def test_fuzz_plane_operations(ac, chunk):
     tcv = ck.best_tcv_checker()
     rng = np.random.default_rng(7700 + chunk)
-    ops = ["clip", "reduce", "flip_v", "flip_h", "gamma", "antialias"]
+    ops = ["clip", "reduce", "flip_v", "flip_h", "gamma", "antialias", "deinterlace", "resize"]
     for case in range(70):
         op = ops[int(rng.integers(0, len(ops)))]
         bpp = 1 if rng.integers(0, 2) else 3
