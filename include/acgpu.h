@@ -88,6 +88,15 @@ int acgpu_imgconvert_batch(uint8_t *const *src, ImageFormat srcfmt, size_t src_f
 int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt,
                                  uint8_t *dest_frames, ImageFormat destfmt,
                                  int width, int height, int nframes);
+/*
+ * The same over several GPUs of one host: frames are independent, so the run is cut into `ndevices` contiguous blocks
+ * (devices 0 .. ndevices-1; ndevices <= 0 = every visible device) and each block goes through its own device's pipeline
+ * on its own internal host thread -- one thread, stream set and staging per device, no exchange between devices.
+ * What transcode's N frame threads do by hand (src/frame_threads.c:174-228), for callers that hold a run of frames.
+ */
+int acgpu_imgconvert_frames_host_multi(const uint8_t *src_frames, ImageFormat srcfmt,
+                                       uint8_t *dest_frames, ImageFormat destfmt,
+                                       int width, int height, int nframes, int ndevices);
 
 /* ---- batched ac_average / ac_rescale ------------------------------------------------------ */
 /*

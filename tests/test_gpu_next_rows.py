@@ -140,3 +140,25 @@ def test_in_place_converts_on_two_streams_share_the_temporary_safely(ac, chk):
     for (_, _, _, _, buf) in jobs:
         buf.free()
     ac.lib.acgpu_stream_destroy(s1); ac.lib.acgpu_stream_destroy(s2)
+
+
+def test_frames_host_multi_splits_a_run_over_the_visible_devices(ac, chk):
+    """acgpu_imgconvert_frames_host_multi: contiguous blocks of a host-frame run go to one device each (own thread,
+    streams and staging), results are byte-identical to the single-device call.  With one visible GPU it degenerates to
+    one block; asking for more devices than exist is refused."""
+    ndev = ac.lib.acgpu_device_count()
+    sf, df, w, h, nf = F.IMG_YUV420P, F.IMG_BGRA32, 640, 360, 23
+    sfb, dfb = F.frame_bytes(sf, w, h), F.frame_bytes(df, w, h)
+    hs, hd = ac.pinned(nf * sfb), ac.pinned(nf * dfb)
+    frames = [ck.random_frame(sf, w, h, seed=900 + i) for i in range(nf)]
+    for i in range(nf):
+        hs.array[i * sfb:(i + 1) * sfb] = frames[i]
+    for use in sorted({1, ndev, 0}):
+        hd.array[:] = 0x5A
+        ac._ok(ac.lib.acgpu_imgconvert_frames_host_multi(hs.ptr, sf, hd.ptr, df, w, h, nf, use))
+        for i in range(nf):
+            want = chk.convert(frames[i], sf, df, w, h, prefill=0x5A, pad=0)[1]
+            assert np.array_equal(hd.array[i * dfb:(i + 1) * dfb], want), (use, i)
+    assert ac.lib.acgpu_imgconvert_frames_host_multi(hs.ptr, sf, hd.ptr, df, w, h, nf, ndev + 1) == 0
+    assert b"visible" in ac.lib.acgpu_last_error()
+    hs.free(); hd.free()

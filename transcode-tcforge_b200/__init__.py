@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "acgpu_malloc", "acgpu_free", "acgpu_host_alloc", "acgpu_host_free", "acgpu_memcpy_h2d",
     "acgpu_memcpy_d2h", "acgpu_memcpy_d2d", "acgpu_memset", "acgpu_stream_create", "acgpu_stream_destroy",
     "acgpu_stream_sync", "acgpu_event_create", "acgpu_event_destroy", "acgpu_event_record",
-    "acgpu_event_sync", "acgpu_event_elapsed_ms", "acgpu_imgconvert_batch", "acgpu_imgconvert_frames_host",
+    "acgpu_event_sync", "acgpu_event_elapsed_ms", "acgpu_imgconvert_batch", "acgpu_imgconvert_frames_host", "acgpu_imgconvert_frames_host_multi",
     "acgpu_rowops_run", "acgpu_average", "acgpu_rescale", "acgpu_deinterlace_batch", "acgpu_resize_batch",
     "acgpu_convert_batch", "acgpu_decolor_rgb24_batch",
     "acgpu_clip_batch", "acgpu_reduce_batch", "acgpu_flip_v_batch", "acgpu_flip_h_batch",
@@ -85,6 +85,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "acgpu_event_elapsed_ms": (C.c_float, [vp, vp]),
         "acgpu_imgconvert_batch": (i32, [C.POINTER(vp), i32, sz, C.POINTER(vp), i32, sz, i32, i32, i32, vp]),
         "acgpu_imgconvert_frames_host": (i32, [vp, i32, vp, i32, i32, i32, i32]),
+        "acgpu_imgconvert_frames_host_multi": (i32, [vp, i32, vp, i32, i32, i32, i32, i32]),
         "acgpu_rowops_run": (i32, [vp, sz, vp, sz, C.POINTER(RowOp), i32, i32, i32, vp]),
         "acgpu_average": (i32, [vp, vp, vp, sz, vp]), "acgpu_rescale": (i32, [vp, vp, vp, sz, u32, u32, vp]),
         "acgpu_deinterlace_batch": (i32, [vp, vp, i32, i32, i32, i32, sz, sz, i32, vp]),

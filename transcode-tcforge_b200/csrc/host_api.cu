@@ -23,6 +23,12 @@
 #include <strings.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 namespace acgpu {
@@ -743,6 +749,95 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
     }
     for (int s = 0; s < kPipeSlots; s++)
         if (!check(cudaStreamSynchronize(c->pipe_stream[s]), "acgpu_imgconvert_frames_host")) return 0;
+    return 1;
+}
+
+// Frames are independent: a run of host frames is cut into contiguous blocks, one per device, and every
+// block goes through that device's own pipeline on its own host thread.  No exchange between devices, no collective.
+// The per-device host threads are long-lived (created on first use, one per device, parked on a condition variable):
+// their streams, pipeline buffers and device contexts persist from call to call.
+}  // extern "C"
+
+namespace acgpu {
+namespace {
+
+struct DeviceWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool pending = false, quit = false;
+
+    DeviceWorker()
+    {
+        th = std::thread([this] {
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return pending || quit; });
+                if (quit) return;
+                lk.unlock();
+                job();
+                lk.lock();
+                pending = false;
+                cv.notify_all();
+            }
+        });
+    }
+    void submit(std::function<void()> f)
+    {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(f);
+        pending = true;
+        cv.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return !pending; });
+    }
+    ~DeviceWorker()
+    {
+        { std::lock_guard<std::mutex> lk(m); quit = true; cv.notify_all(); }
+        if (th.joinable()) th.join();
+    }
+};
+
+std::mutex g_multi_mutex;                                     // one multi-device call at a time
+std::unique_ptr<DeviceWorker> g_workers[kMaxDev];
+
+}  // namespace
+}  // namespace acgpu
+
+extern "C" {
+
+int acgpu_imgconvert_frames_host_multi(const uint8_t *src_frames, ImageFormat srcfmt, uint8_t *dest_frames,
+                                       ImageFormat destfmt, int width, int height, int nframes, int ndevices)
+{
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) { cudaGetLastError(); set_error("no CUDA device"); return 0; }
+    if (ndevices <= 0) ndevices = visible;
+    if (ndevices > visible || ndevices > kMaxDev) { set_error("acgpu_imgconvert_frames_host_multi: %d devices requested, %d visible", ndevices, visible); return 0; }
+    const int sf = srcfmt == IMG_YV12 ? IMG_YUV420P : (int)srcfmt, df = destfmt == IMG_YV12 ? IMG_YUV420P : (int)destfmt;
+    if (describe(sf).kind == K_NONE || describe(df).kind == K_NONE) { set_error("unknown format pair"); return 0; }
+    if (width <= 0 || height <= 0 || nframes <= 0) return 1;
+    if (ndevices > nframes) ndevices = nframes;
+    const size_t sfb = frame_bytes(sf, width, height), dfb = frame_bytes(df, width, height);
+    std::lock_guard<std::mutex> call(g_multi_mutex);
+    std::vector<int> ok((size_t)ndevices, 0);
+    std::vector<std::string> why((size_t)ndevices);
+    for (int d = 0; d < ndevices; d++) {
+        if (!g_workers[d]) g_workers[d].reset(new DeviceWorker());
+        const int f0 = (int)((int64_t)nframes * d / ndevices), f1 = (int)((int64_t)nframes * (d + 1) / ndevices);
+        g_workers[d]->submit([=, &ok, &why] {
+            ok[(size_t)d] = acgpu_set_device(d)
+                         && acgpu_imgconvert_frames_host(src_frames + (size_t)f0 * sfb, srcfmt, dest_frames + (size_t)f0 * dfb, destfmt,
+                                                         width, height, f1 - f0);
+            if (!ok[(size_t)d]) why[(size_t)d] = tls.err;
+        });
+    }
+    for (int d = 0; d < ndevices; d++) g_workers[d]->wait();
+    for (int d = 0; d < ndevices; d++)
+        if (!ok[(size_t)d]) { set_error("device %d: %s", d, why[(size_t)d].c_str()); return 0; }
     return 1;
 }
 
