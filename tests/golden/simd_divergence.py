@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Regenerates SURVEY.md Appendix B: where aclib's SSE2 path differs from its own plain-C path (CPU only).
 
-    python tools/simd_divergence.py > profiles/r1_reference_simd_vs_c.md
+    python tests/golden/simd_divergence.py > profiles/r1_reference_simd_vs_c.md
+(TEST INFRASTRUCTURE: it loads the reference builds under oracle/_ref, like the other scripts in this directory.)
 Both libraries are the unmodified reference (oracle/_ref).  768x512 uniform-random bytes, dest pre-filled 0x55.
 libacgpu's parity target is the C path; this table documents what a user switching from --accel sse2 will see.
 """
@@ -10,7 +11,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 import checkers as ck  # noqa: E402
