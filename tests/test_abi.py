@@ -128,3 +128,10 @@ def test_product_never_touches_the_oracle():
                     assert needle not in text, f"{f} references {needle}"
     out = subprocess.run(["ldd", pkg.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "libac_ref" not in out
+    # the profiling aids under tools/ drive the product only; scripts that need the reference live under tests/
+    tools = os.path.join(ROOT, "tools")
+    for f in os.listdir(tools):
+        if f.endswith((".py", ".sh", ".c", ".cu")):
+            text = open(os.path.join(tools, f), errors="ignore").read()
+            for needle in ("liboracle", "ac_oracle", "oracle_", "oracle/", "libac_ref", "libtcv_ref", "import checkers"):
+                assert needle not in text, f"tools/{f} references {needle}"
