@@ -399,7 +399,9 @@ def test_ragged_420_widths_use_the_vectorised_tier(ac, chk):
     """4:2:0 frames whose width is not a multiple of 16 (854x480, 1080-wide portrait, the reference test's 766):
     rows are no longer 16-byte aligned, so YUV420P <-> RGB walks flat 16-pixel units and reaches the chroma rows with
     byte-aligned accesses (S420R / D420R); units that run over the end of a row fetch/store sample by sample."""
-    sizes = [(854, 480, 1), (1080, 40, 2), (766, 32, 1), (40, 8, 3), (50, 16, 2), (18, 16, 2), (24, 2, 1), (426, 240, 1)]
+    # the last two: widths on the 16-pixel grid whose V plane is still not 16-byte aligned (width*height % 64 != 0)
+    sizes = [(854, 480, 1), (1080, 40, 2), (766, 32, 1), (40, 8, 3), (50, 16, 2), (18, 16, 2), (24, 2, 1), (426, 240, 1),
+             (48, 10, 1), (1936, 10, 1)]
     for (w, h, nf) in sizes:
         for rf in RGB_ALL:
             for sf, df in ((F.IMG_YUV420P, rf), (rf, F.IMG_YUV420P), (F.IMG_YV12, rf), (rf, F.IMG_YV12)):
@@ -419,7 +421,8 @@ def test_ragged_420_widths_yuv_family(ac, chk):
     from an odd row into an even one contributes only its tail to the vertical chroma mean."""
     others = [F.IMG_YUV422P, F.IMG_YUV444P, F.IMG_YUV411P, F.IMG_YUY2, F.IMG_UYVY, F.IMG_YVYU, F.IMG_Y8, F.IMG_GRAY8,
               F.IMG_YUV420P, F.IMG_YV12]
-    sizes = [(854, 480, 1), (1080, 40, 2), (766, 32, 1), (40, 8, 3), (50, 16, 2), (18, 16, 2), (24, 2, 1), (426, 240, 1), (20, 4, 2)]
+    sizes = [(854, 480, 1), (1080, 40, 2), (766, 32, 1), (40, 8, 3), (50, 16, 2), (18, 16, 2), (24, 2, 1), (426, 240, 1), (20, 4, 2),
+             (48, 10, 1), (1936, 10, 1)]
     for (w, h, nf) in sizes:
         for o in others:
             for sf, df in ((F.IMG_YUV420P, o), (o, F.IMG_YUV420P)):

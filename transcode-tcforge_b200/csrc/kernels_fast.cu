@@ -752,7 +752,10 @@ static bool fast_domain(const ConvertArgs &a, FastParams *out)
     const size_t P = (size_t)w * h;
     // every plane 16-byte aligned -- except the chroma planes of a ragged 4:2:0 frame, which are reached through
     // byte-aligned accesses anyway (e.g. 50x16: V starts at byte 1000 of the frame)
-    const bool ragged_w = any420 && w % 16;
+    // (the same kernels take an aligned width whose 4:2:0 chroma planes are not 16-byte aligned: width*height % 64 != 0)
+    const bool chroma_off = (a.srcfmt == IMG_YUV420P && !(al16(a.src.p[1]) && al16(a.src.p[2])))
+                         || (a.dstfmt == IMG_YUV420P && !(al16(a.dst.p[1]) && al16(a.dst.p[2])));
+    const bool ragged_w = any420 && (w % 16 || chroma_off);
     for (int i = 0; i < 3; i++) {
         const bool s_free = ragged_w && i > 0 && a.srcfmt == IMG_YUV420P, d_free = ragged_w && i > 0 && a.dstfmt == IMG_YUV420P;
         if (a.src.p[i] && (s_free ? ((uintptr_t)a.src.p[i] & 3) != 0 : !al16(a.src.p[i]))) return false;
@@ -761,7 +764,7 @@ static bool fast_domain(const ConvertArgs &a, FastParams *out)
     bool ragged = false;
     if (any420) {
         if (w % 2 || h % 2) return false;
-        if (w % 16) {
+        if (ragged_w) {
             // ragged 4:2:0 rows: flat-unit kernels (S420R / D420R in this file, Ragged420From / Ragged420To in
             // kernels_fast_yuv.cu); 4:1:1 needs whole 4-pixel groups per row
             const int other = a.srcfmt == IMG_YUV420P ? a.dstfmt : a.srcfmt;
