@@ -173,3 +173,67 @@ def test_table_cache_eviction_never_frees_a_table_in_use(ac, tcv):
         nw = width + rw * 8
         ok, got = ac.plane_op_batch("resize", s2[None, :], nw * h * bpp, width, h, bpp, rw, 0, 8, 8)
         assert ok == 1 and np.array_equal(got[0], tcv.resize(s2, width, h, bpp, rw, 0, 8, 8)), ("resize", i, width, nw)
+
+
+def _model_rowop(src, op, n):
+    """numpy statement of one acgpu_rowop (aclib/rescale.c:23-46, average.c:33-39) on a flat source plane."""
+    a = src[op.src1_off: op.src1_off + n].astype(np.uint64)
+    if op.op == pkg.ACGPU_ROW_COPY:
+        return a.astype(np.uint8)
+    b = src[op.src2_off: op.src2_off + n].astype(np.uint64)
+    if op.op == pkg.ACGPU_ROW_AVERAGE:
+        return ((a + b + 1) >> 1).astype(np.uint8)
+    if op.op == pkg.ACGPU_ROW_AVERAGE3:
+        c = src[op.src3_off: op.src3_off + n].astype(np.uint64)
+        return ((c + ((a + b + 1) >> 1) + 1) >> 1).astype(np.uint8)
+    if op.weight1 >= 0x10000:
+        return a.astype(np.uint8)
+    if op.weight2 >= 0x10000:
+        return b.astype(np.uint8)
+    return (((a * op.weight1 + b * op.weight2 + 32768) & 0xFFFFFFFF) >> 16).astype(np.uint8)
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+def test_rowops_run_with_caller_built_tables(ac, aligned):
+    """acgpu_rowops_run directly: random tables of all four operations, weights on both sides of 65536 (the copy
+    branches must not read the other row: its offset points far outside the plane), rows at aligned offsets (tiled
+    cp.async kernel) or byte offsets (byte kernel), several frames with a pitch gap."""
+    rng = np.random.default_rng(321 + aligned)
+    for trial in range(12):
+        row = int(rng.integers(1, 40)) * 16 if aligned else int(rng.integers(1, 700))
+        rows_src, nops, nf = int(rng.integers(3, 40)), int(rng.integers(1, 60)), int(rng.integers(1, 4))
+        step = row if aligned else row + int(rng.integers(0, 5))
+        sfb = rows_src * step + row
+        dfb = nops * step + row
+        spitch = sfb + (32 if aligned else 7)
+        dpitch = dfb + (48 if aligned else 11)
+        frames = [ck.splitmix_bytes(sfb, 1000 * trial + i) for i in range(nf)]
+        ops = (pkg.RowOp * nops)()
+        far = 1 << 40                                     # never dereferenced
+        for k in range(nops):
+            o = ops[k]
+            o.op = int(rng.integers(0, 4))
+            o.src1_off, o.src2_off, o.src3_off = (int(rng.integers(0, rows_src)) * step for _ in range(3))
+            o.dest_off = k * step
+            w1 = int(rng.choice([0, 1, 32768, 49152, 65535, 65536, 70000, int(rng.integers(0, 65536))]))
+            o.weight1, o.weight2 = w1, int(rng.choice([65536 - min(w1, 65536), 65536, int(rng.integers(0, 65536))]))
+            if o.op == pkg.ACGPU_ROW_RESCALE and o.weight1 >= 0x10000:
+                o.src2_off = far
+            elif o.op == pkg.ACGPU_ROW_RESCALE and o.weight2 >= 0x10000:
+                o.src1_off = far
+            elif o.op == pkg.ACGPU_ROW_COPY:
+                o.src2_off = o.src3_off = far
+        hs = np.full(nf * spitch, 0x33, np.uint8)
+        for i in range(nf):
+            hs[i * spitch: i * spitch + sfb] = frames[i]
+        dsrc = ac.malloc(hs.size).upload(hs)
+        ddst = ac.malloc(nf * dpitch).fill(0x77)
+        ac._ok(ac.lib.acgpu_rowops_run(dsrc.ptr, spitch, ddst.ptr, dpitch, ops, nops, row, nf, None))
+        ac.sync()
+        got = ddst.download().reshape(nf, dpitch)
+        for i in range(nf):
+            want = np.full(dpitch, 0x77, np.uint8)
+            for k in range(nops):
+                want[ops[k].dest_off: ops[k].dest_off + row] = _model_rowop(frames[i], ops[k], row)
+            assert np.array_equal(got[i], want), (aligned, trial, i)
+        dsrc.free(); ddst.free()

@@ -32,6 +32,11 @@ _u8p = C.POINTER(C.c_uint8)
 _planes_t = _u8p * 3
 
 
+# include/acgpu.h row-operation codes and deinterlace modes
+ACGPU_ROW_RESCALE, ACGPU_ROW_AVERAGE, ACGPU_ROW_COPY, ACGPU_ROW_AVERAGE3 = 0, 1, 2, 3
+ACGPU_DEINT_INTERPOLATE, ACGPU_DEINT_LINEAR_BLEND, ACGPU_DEINT_DROP_FIELD_TOP, ACGPU_DEINT_DROP_FIELD_BOTTOM = 0, 1, 2, 3
+
+
 class RowOp(C.Structure):
     _fields_ = [("src1_off", C.c_int64), ("src2_off", C.c_int64), ("src3_off", C.c_int64),
                 ("dest_off", C.c_int64), ("weight1", C.c_uint32), ("weight2", C.c_uint32),
