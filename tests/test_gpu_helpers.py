@@ -98,3 +98,24 @@ def test_device_pointer_average_and_rescale(ac):
         assert np.array_equal(out.download(n), b)
     L.acgpu_stream_destroy(st)
     buf.free(); out.free()
+
+
+def test_ac_memcpy_on_device_memory_is_memmove(ac):
+    """aclib/memcpy.c:16-25 is memmove (ac.h:80-82 promises the ascending-copy behaviour callers rely on for overlapping
+    buffers); device-to-device copies keep that for overlapping ranges in both directions, and mixed host/device work."""
+    L = ac.lib
+    n = 100000
+    a = ck.splitmix_bytes(n, 12)
+    for (dst_off, src_off, size) in [(0, 1000, 50000), (1000, 0, 50000), (5, 4, 99000), (0, 60000, 30000)]:
+        buf = ac.malloc(n).upload(a)
+        assert L.ac_memcpy(buf.ptr + dst_off, buf.ptr + src_off, size) == buf.ptr + dst_off
+        want = a.copy()
+        want[dst_off:dst_off + size] = a[src_off:src_off + size]
+        assert np.array_equal(buf.download(), want), (dst_off, src_off, size)
+        buf.free()
+    buf = ac.malloc(n)
+    assert L.ac_memcpy(buf.ptr, a.ctypes.data, n) == buf.ptr                    # host -> device
+    back = np.zeros(n, np.uint8)
+    assert L.ac_memcpy(back.ctypes.data, buf.ptr, n) == back.ctypes.data        # device -> host
+    assert np.array_equal(back, a)
+    buf.free()

@@ -511,9 +511,19 @@ void *ac_memcpy(void *dest, const void *src, size_t size)
     const PtrKind kd = classify(dest), ks = classify(src);
     if (kd != PK_DEVICE && ks != PK_DEVICE) return memmove(dest, src, size);
     DevCtx *c = ctx();
-    if (!c || !check(cudaMemcpyAsync(dest, src, size, cudaMemcpyDefault, c->stream), "ac_memcpy")
-        || !check(cudaStreamSynchronize(c->stream), "ac_memcpy"))
-        fatal("ac_memcpy");
+    if (!c) fatal("ac_memcpy");
+    const uint8_t *s = static_cast<const uint8_t *>(src);
+    uint8_t *d = static_cast<uint8_t *>(dest);
+    bool ok;
+    if (kd == PK_DEVICE && ks == PK_DEVICE && s < d + size && d < s + size) {
+        // overlapping device ranges: memmove semantics through the thread's temporary (a plain device copy is undefined)
+        ok = ensure_arena(c, size) && arena_acquire(c, c->stream)
+          && check(cudaMemcpyAsync(c->arena, src, size, cudaMemcpyDeviceToDevice, c->stream), "ac_memcpy")
+          && check(cudaMemcpyAsync(dest, c->arena, size, cudaMemcpyDeviceToDevice, c->stream), "ac_memcpy");
+    } else {
+        ok = check(cudaMemcpyAsync(dest, src, size, cudaMemcpyDefault, c->stream), "ac_memcpy");
+    }
+    if (!ok || !check(cudaStreamSynchronize(c->stream), "ac_memcpy")) fatal("ac_memcpy");
     return dest;
 }
 
