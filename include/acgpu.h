@@ -126,7 +126,12 @@ int acgpu_average(const uint8_t *src1, const uint8_t *src2, uint8_t *dest, size_
 int acgpu_rescale(const uint8_t *src1, const uint8_t *src2, uint8_t *dest, size_t bytes,
                   uint32_t weight1, uint32_t weight2, acgpu_stream_t stream);
 
-/* ---- frame-granular libtcvideo shapes (device-resident) ----------------------------------- */
+/* ---- frame-granular libtcvideo shapes ----------------------------------------------------------
+ * Written for device-resident planes (asynchronous on `stream`).  src and/or dest may also be HOST memory, pageable or
+ * page-locked -- what an unmodified libtcvideo caller holds: the batch is then uploaded once, processed on the device
+ * and downloaded once through the calling thread's staging arena, and the call returns after the result has landed
+ * (one round trip per frame instead of the one per ROW that tcv_deinterlace / tcv_resize make through ac_average /
+ * ac_rescale).  The same holds for the element-wise operations further down. */
 enum { ACGPU_DEINT_INTERPOLATE = 0, ACGPU_DEINT_LINEAR_BLEND = 1, ACGPU_DEINT_DROP_FIELD_TOP = 2, ACGPU_DEINT_DROP_FIELD_BOTTOM = 3 };
 /* tcv_deinterlace (libtcvideo/tcvideo.c:290-389), all four modes, on nframes frames of width x height x Bpp bytes.
  * The drop-field modes write height/2 rows (tcvideo.c:326-338).  Unlike the reference's linear blend, src is left intact. */

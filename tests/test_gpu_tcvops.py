@@ -228,3 +228,60 @@ def test_concurrent_threads_each_with_their_own_tables(ac):
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert not errors, errors
+
+
+@pytest.mark.parametrize("kind", ["pageable", "pinned", "mixed"])
+def test_host_frames_are_staged_once_per_call(ac, tcv, kind):
+    """The frame-granular entry points also take HOST planes (what an unmodified libtcvideo caller holds): the batch is
+    uploaded once, processed on the device, downloaded once, and the call returns with the result in place.  Pageable,
+    page-locked and mixed (host source, device destination and the reverse) combinations; two planes per call with
+    gaps between them that must stay untouched."""
+    L = ac.lib
+    nf = 2
+    for case in tcv_cases.cases():
+        key, op, (w, h, bpp), args, img_kind, seed = case
+        if (w, h) not in ((64, 16), (33, 7), (64, 48), (32, 16)) or (op in ("flip_v", "flip_h") and args[0] and kind == "mixed"):
+            continue
+        inplace = op in ("flip_v", "flip_h") and args[0]
+        call_args = () if op in ("flip_v", "flip_h") else args
+        frames = [tcv_cases.image(img_kind, w, h, bpp, seed + 1000 * i) for i in range(nf)]
+        refs = [tcv_cases.run_case(tcv, (key, op, (w, h, bpp), args, img_kind, seed + 1000 * i)) for i in range(nf)]
+        ok_ref = refs[0][0]
+        nout = out_bytes(op, w, h, bpp, args)
+        sfb = w * h * bpp
+        spitch, dpitch = sfb + 5, (sfb + 5 if inplace else nout + 9)
+        hs = np.full(nf * spitch, 0x21, np.uint8)
+        for i in range(nf):
+            hs[i * spitch: i * spitch + sfb] = frames[i]
+        hd = hs if inplace else np.full(max(nf * dpitch, 1), 0x55, np.uint8)
+        keep = []
+        if kind == "pinned":
+            ps, pd = ac.pinned(hs.size), ac.pinned(hd.size)
+            ps.array[:] = hs
+            pd.array[:] = hd
+            sptr, dptr = ps.ptr, (ps.ptr if inplace else pd.ptr)
+            read = (lambda: ps.array.copy()) if inplace else (lambda: pd.array.copy())
+            keep = [ps, pd]
+        elif kind == "mixed" and (seed & 1):
+            dsrc = ac.malloc(hs.size).upload(hs)                  # device source, pageable destination
+            sptr, dptr, read = dsrc.ptr, hd.ctypes.data, (lambda: hd.copy())
+            keep = [dsrc]
+        elif kind == "mixed":
+            ddst = ac.malloc(hd.size).upload(hd)                  # pageable source, device destination
+            sptr, dptr, read = hs.ctypes.data, ddst.ptr, ddst.download
+            keep = [ddst]
+        else:
+            sptr, dptr = hs.ctypes.data, (hs.ctypes.data if inplace else hd.ctypes.data)
+            read = (lambda: hs.copy()) if inplace else (lambda: hd.copy())
+        fn = getattr(L, f"acgpu_{OPS.get(op, op)}_batch")
+        ok = fn(sptr, dptr, w, h, bpp, *call_args, spitch, dpitch, nf, None)
+        assert ok == ok_ref, (key, kind, ac.last_error())
+        if ok:
+            got = read()
+            ac.sync()
+            for i in range(nf):
+                assert np.array_equal(got[i * dpitch: i * dpitch + nout], refs[i][1][:nout]), (key, kind, i)
+                gap = got[i * dpitch + nout: (i + 1) * dpitch]
+                assert (gap == (0x21 if inplace else 0x55)).all(), (key, kind, "gap written")
+        for k in keep:
+            k.free()

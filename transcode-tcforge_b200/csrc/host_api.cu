@@ -102,6 +102,7 @@ PtrKind classify(const void *p)
 }
 
 }  // namespace
+bool is_device_pointer(const void *p) { return classify(p) == PK_DEVICE; }
 bool ensure_arena(DevCtx *c, size_t bytes)
 {
     if (bytes <= c->arena_cap) return true;

@@ -69,6 +69,7 @@ extern thread_local ThreadCtx tls;
 
 DevCtx      *ctx();                                            // binds the thread's device, creates its stream on first use
 cudaStream_t pick_stream(DevCtx *c, acgpu_stream_t s);         // the caller's stream, or the thread's own
+bool  is_device_pointer(const void *p);                        // device / managed memory (else pageable or page-locked host)
 bool  ensure_arena(DevCtx *c, size_t bytes);
 bool  arena_acquire(DevCtx *c, cudaStream_t st);               // orders uses of the arena on different streams
 bool  arena_release(DevCtx *c, cudaStream_t st);

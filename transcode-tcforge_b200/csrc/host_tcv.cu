@@ -33,6 +33,56 @@ void build_resize_table(int oldsize, int newsize, std::vector<int32_t> &src, std
     }
 }
 
+// Host frames for the frame-granular entry points.  These functions are written for device-resident planes; when the
+// caller's source and/or destination is host memory (unmodified libtcvideo callers hold host frame buffers) the planes go
+// through the thread's device arena: one upload of the batch, the operation on the device copies, one download, and the
+// call returns after the result has landed -- the same contract as the legacy per-frame ac_imgconvert path, but one
+// round trip per FRAME instead of one per ROW (tcv_deinterlace / tcv_resize call ac_average / ac_rescale per row).
+struct HostStage {
+    DevCtx *c = nullptr;
+    bool staged = false, ok = true, dst_host = false;
+    const uint8_t *dsrc = nullptr;
+    uint8_t *ddst = nullptr, *dest = nullptr;
+    size_t dsp = 0, ddp = 0, dp_host = 0, out_bytes = 0;
+    int nf = 0;
+
+    HostStage(const uint8_t *src, size_t in_bytes, size_t spitch, uint8_t *dst, size_t outb, size_t dpitch, int nframes)
+    {
+        if (nframes <= 0) return;
+        const bool src_host = !is_device_pointer(src);
+        dst_host = !is_device_pointer(dst);
+        if (!src_host && !dst_host) return;
+        staged = true;
+        c = ctx();
+        if (!c) { ok = false; return; }
+        dest = dst; out_bytes = outb; nf = nframes;
+        const size_t sp_host = spitch ? spitch : in_bytes;
+        dp_host = dpitch ? dpitch : outb;
+        const bool in_place = static_cast<const void *>(src) == static_cast<const void *>(dst);
+        dsp = src_host ? align_up(in_place && outb > in_bytes ? outb : in_bytes, 256) : sp_host;    // in place: room for the larger side
+        ddp = in_place ? dsp : dst_host ? align_up(outb, 256) : dp_host;
+        const size_t src_region = src_host ? dsp * (size_t)nframes : 0, dst_region = (dst_host && !in_place) ? ddp * (size_t)nframes : 0;
+        if (!ensure_arena(c, src_region + dst_region + 256) || !arena_acquire(c, c->stream)) { ok = false; return; }
+        uint8_t *as = c->arena, *ad = c->arena + src_region;
+        if (src_host) {
+            ok = check(cudaMemcpy2DAsync(as, dsp, src, sp_host, in_bytes, (size_t)nframes, cudaMemcpyHostToDevice, c->stream), "H2D planes");
+            dsrc = as;
+        } else {
+            dsrc = src;
+        }
+        ddst = in_place ? const_cast<uint8_t *>(dsrc) : dst_host ? ad : dst;
+    }
+    acgpu_stream_t stream() const { return reinterpret_cast<acgpu_stream_t>(c->stream); }
+    int finish(int launched)
+    {
+        bool good = ok && launched;
+        if (good && dst_host && out_bytes)
+            good = check(cudaMemcpy2DAsync(dest, dp_host, ddst, ddp, out_bytes, (size_t)nf, cudaMemcpyDeviceToHost, c->stream), "D2H planes");
+        if (c) good = check(cudaStreamSynchronize(c->stream), "frame operation") && good;
+        return good ? 1 : 0;
+    }
+};
+
 }  // namespace
 }  // namespace acgpu
 
@@ -48,6 +98,12 @@ int acgpu_deinterlace_batch(const uint8_t *src, uint8_t *dest, int width, int he
     if (!src || !dest || width <= 0 || height <= 0 || (Bpp != 1 && Bpp != 3)) { set_error("acgpu_deinterlace_batch: invalid frame parameters"); return 0; }
     if (mode < ACGPU_DEINT_INTERPOLATE || mode > ACGPU_DEINT_DROP_FIELD_BOTTOM) { set_error("acgpu_deinterlace_batch: invalid mode %d", mode); return 0; }
     const int64_t Bpl = (int64_t)width * Bpp;
+    {
+        const bool drop = mode == ACGPU_DEINT_DROP_FIELD_TOP || mode == ACGPU_DEINT_DROP_FIELD_BOTTOM;
+        HostStage hs(src, (size_t)Bpl * height, spitch, dest, (size_t)Bpl * (drop ? height / 2 : height), dpitch, nframes);
+        if (hs.staged)
+            return hs.finish(hs.ok && acgpu_deinterlace_batch(hs.dsrc, hs.ddst, width, height, Bpp, mode, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     if (mode == ACGPU_DEINT_DROP_FIELD_TOP || mode == ACGPU_DEINT_DROP_FIELD_BOTTOM) {
         // tcvideo.c:326-338: keep every other line, starting at line 1 when the top field is dropped
         std::vector<acgpu_rowop> ops((size_t)(height / 2));
@@ -93,6 +149,12 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     if (resize_w && resize_h) { set_error("acgpu_resize_batch: only one of resize_w / resize_h may be non-zero"); return 0; }
     const int new_w = width + resize_w * scale_w, new_h = height + resize_h * scale_h;
     if (new_w <= 0 || new_h <= 0) { set_error("acgpu_resize_batch: resulting size is not positive"); return 0; }
+    {
+        HostStage hs(src, (size_t)width * height * Bpp, spitch, dest, (size_t)new_w * new_h * Bpp, dpitch, nframes);
+        if (hs.staged)
+            return hs.finish(hs.ok && acgpu_resize_batch(hs.dsrc, hs.ddst, width, height, Bpp, resize_w, resize_h, scale_w, scale_h,
+                                                         hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     DevCtx *c = ctx();
     if (!c) return 0;
     cudaStream_t st = pick_stream(c, stream);
@@ -269,6 +331,12 @@ int acgpu_clip_batch(const uint8_t *src, uint8_t *dest, int width, int height, i
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    {
+        HostStage hs(src, (size_t)width * height * Bpp, spitch, dest, (size_t)(new_w * new_h * Bpp), dpitch, nframes);
+        if (hs.staged)
+            return hs.finish(hs.ok && acgpu_clip_batch(hs.dsrc, hs.ddst, width, height, Bpp, clip_left, clip_right, clip_top, clip_bottom,
+                                                       black_pixel, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     TcvWindow p{};
     p.src = src; p.spitch = spitch; p.dst = dest; p.dpitch = dpitch;
     p.dBpl = (uint32_t)(new_w * Bpp); p.sBpl = (uint32_t)width * Bpp;
@@ -294,6 +362,12 @@ int acgpu_reduce_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    {
+        const size_t outb = (size_t)(reduce_w != 1 ? width / reduce_w : width) * (size_t)(height / reduce_h) * Bpp;
+        HostStage hs(src, (size_t)width * height * Bpp, spitch, dest, outb, dpitch, nframes);
+        if (hs.staged)
+            return hs.finish(hs.ok && acgpu_reduce_batch(hs.dsrc, hs.ddst, width, height, Bpp, reduce_w, reduce_h, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     cudaStream_t st = pick_stream(c, stream);
     if (reduce_w != 1)      // tcvideo.c:694-704
         return per_frame_chunk(nframes, [&](int f0, int nf) {
@@ -321,6 +395,11 @@ int acgpu_flip_v_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    {
+        const size_t fb = (size_t)width * height * Bpp;
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (hs.staged) return hs.finish(hs.ok && acgpu_flip_v_batch(hs.dsrc, hs.ddst, width, height, Bpp, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     cudaStream_t st = pick_stream(c, stream);
     return per_frame_chunk(nframes, [&](int f0, int nf) {
         return tcv_flip_v_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, width, height, Bpp, nf, st);
@@ -334,6 +413,11 @@ int acgpu_flip_h_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    {
+        const size_t fb = (size_t)width * height * Bpp;
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (hs.staged) return hs.finish(hs.ok && acgpu_flip_h_batch(hs.dsrc, hs.ddst, width, height, Bpp, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     cudaStream_t st = pick_stream(c, stream);
     return per_frame_chunk(nframes, [&](int f0, int nf) {
         return tcv_flip_h_launch(src + (size_t)f0 * spitch, spitch, dest + (size_t)f0 * dpitch, dpitch, width, height, Bpp, nf, st);
@@ -348,6 +432,11 @@ int acgpu_gamma_correct_batch(const uint8_t *src, uint8_t *dest, int width, int 
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    {
+        const size_t fb = (size_t)width * height * Bpp;
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (hs.staged) return hs.finish(hs.ok && acgpu_gamma_correct_batch(hs.dsrc, hs.ddst, width, height, Bpp, gamma, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     cudaStream_t st = pick_stream(c, stream);
     uint8_t table[256];
     for (int i = 0; i < 256; i++) table[i] = (uint8_t)(pow((i / 255.0), gamma) * 255);    // tcvideo.c:1180-1189, host doubles
@@ -370,6 +459,11 @@ int acgpu_antialias_batch(const uint8_t *src, uint8_t *dest, int width, int heig
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    {
+        const size_t fb = (size_t)width * height * Bpp;
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (hs.staged) return hs.finish(hs.ok && acgpu_antialias_batch(hs.dsrc, hs.ddst, width, height, Bpp, weight, bias, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     cudaStream_t st = pick_stream(c, stream);
     uint32_t t[1024];     // c | x | y | d, tcvideo.c:1209-1224 (double -> uint32 truncation, evaluation order kept)
     for (int i = 0; i < 256; i++) {
