@@ -162,3 +162,20 @@ def test_frames_host_multi_splits_a_run_over_the_visible_devices(ac, chk):
     assert ac.lib.acgpu_imgconvert_frames_host_multi(hs.ptr, sf, hd.ptr, df, w, h, nf, ndev + 1) == 0
     assert b"visible" in ac.lib.acgpu_last_error()
     hs.free(); hd.free()
+
+
+def test_decolor_on_host_frames(ac, chk):
+    """-K on host RGB24 frames (src/video_trans.c:381-388 works on the host vframe buffer): staged once per call."""
+    w, h, nf = 320, 48, 3
+    fb = w * h * 3
+    pitch = fb + 7
+    frames = [ck.random_frame(F.IMG_RGB24, w, h, seed=70 + i) for i in range(nf)]
+    host = np.full(nf * pitch, 0x42, np.uint8)
+    for i in range(nf):
+        host[i * pitch: i * pitch + fb] = frames[i]
+    ac._ok(ac.lib.acgpu_decolor_rgb24_batch(host.ctypes.data, w, h, pitch, nf, None))
+    for i in range(nf):
+        gray = chk.convert(frames[i], F.IMG_RGB24, F.IMG_GRAY8, w, h, pad=0)[1]
+        want = chk.convert(gray, F.IMG_GRAY8, F.IMG_RGB24, w, h, pad=0)[1]
+        assert np.array_equal(host[i * pitch: i * pitch + fb], want), i
+        assert (host[i * pitch + fb: (i + 1) * pitch] == 0x42).all()

@@ -289,6 +289,11 @@ int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t pit
     if (!c) return 0;
     if (!frames || width <= 0 || height <= 0) { set_error("acgpu_decolor_rgb24_batch: invalid frame parameters"); return 0; }
     if (nframes <= 0) return 1;
+    {
+        const size_t fb = (size_t)width * height * 3;
+        HostStage hs(frames, fb, pitch, frames, fb, pitch, nframes);
+        if (hs.staged) return hs.finish(hs.ok && acgpu_decolor_rgb24_batch(hs.ddst, width, height, hs.ddp, nframes, hs.stream()));
+    }
     cudaStream_t st = pick_stream(c, stream);
     if (tls.force_tier != 1 && per_frame_chunk(nframes, [&](int f0, int nf) {
             return decolor_rgb24_fast(frames + (size_t)f0 * pitch, pitch, width, height, nf, st); })) { tls.last_tier = 2; return 1; }
