@@ -166,7 +166,11 @@ def test_frames_host_multi_splits_a_run_over_the_visible_devices(ac, chk):
 
 def test_decolor_on_host_frames(ac, chk):
     """-K on host RGB24 frames (src/video_trans.c:381-388 works on the host vframe buffer): staged once per call."""
-    w, h, nf = 320, 48, 3
+    for (w, h, nf) in [(320, 48, 3), (37, 5, 2)]:       # the second size takes the two-step fallback (temporary gray plane)
+        _decolor_host_case(ac, chk, w, h, nf)
+
+
+def _decolor_host_case(ac, chk, w, h, nf):
     fb = w * h * 3
     pitch = fb + 7
     frames = [ck.random_frame(F.IMG_RGB24, w, h, seed=70 + i) for i in range(nf)]
@@ -179,3 +183,27 @@ def test_decolor_on_host_frames(ac, chk):
         want = chk.convert(gray, F.IMG_GRAY8, F.IMG_RGB24, w, h, pad=0)[1]
         assert np.array_equal(host[i * pitch: i * pitch + fb], want), i
         assert (host[i * pitch + fb: (i + 1) * pitch] == 0x42).all()
+
+
+def test_convert_batch_on_host_frames(ac, chk):
+    """acgpu_convert_batch with host frames (tcv_convert's callers hold host buffers): staged once per call; bytes the C
+    path leaves alone (alpha of YUV -> 32-bit RGB) survive because the host destination is uploaded first; src == dest
+    converts in place like tcvideo.c:1044-1064."""
+    w, h, nf = 96, 20, 3
+    for sf, df in [(F.IMG_YUV420P, F.IMG_ARGB32), (F.IMG_RGB24, F.IMG_YUV422P), (F.IMG_YUY2, F.IMG_YUV420P)]:
+        sfb, dfb = F.frame_bytes(sf, w, h), F.frame_bytes(df, w, h)
+        frames = np.stack([ck.random_frame(sf, w, h, seed=55 + i) for i in range(nf)])
+        hs = frames.reshape(-1).copy()
+        hd = np.full(nf * dfb, 0x9D, np.uint8)
+        ac._ok(ac.lib.acgpu_convert_batch(hs.ctypes.data, hd.ctypes.data, w, h, sf, df, sfb, dfb, nf, None))
+        for i in range(nf):
+            assert np.array_equal(hd[i * dfb:(i + 1) * dfb], chk.convert(frames[i], sf, df, w, h, prefill=0x9D, pad=0)[1]), (sf, df, i)
+        assert np.array_equal(hs, frames.reshape(-1))
+    sf, df = F.IMG_RGB24, F.IMG_YUV420P                       # in place on the host
+    sfb, dfb = F.frame_bytes(sf, w, h), F.frame_bytes(df, w, h)
+    frames = np.stack([ck.random_frame(sf, w, h, seed=65 + i) for i in range(nf)])
+    buf = frames.reshape(-1).copy()
+    ac._ok(ac.lib.acgpu_convert_batch(buf.ctypes.data, buf.ctypes.data, w, h, sf, df, sfb, sfb, nf, None))
+    for i in range(nf):
+        assert np.array_equal(buf[i * sfb: i * sfb + dfb], chk.convert(frames[i], sf, df, w, h, pad=0)[1])
+        assert np.array_equal(buf[i * sfb + dfb:(i + 1) * sfb], frames[i, dfb:])

@@ -25,6 +25,8 @@ struct DevCtx {
     uint8_t *arena = nullptr;            // device staging for the legacy host-pointer calls
     size_t   arena_cap = 0;
     cudaEvent_t arena_ev = nullptr;      // recorded after the last asynchronous use of the arena (see arena_acquire)
+    uint8_t *plane_stage = nullptr;      // device copies of HOST planes handed to the frame-granular entry points (its own
+    size_t   plane_stage_cap = 0;        // buffer: those entry points may use the arena as their temporary meanwhile)
     uint8_t *bounce = nullptr;           // pinned host mirror of the arena (pageable caller buffers go through it)
     size_t   bounce_cap = 0;
     std::vector<Blob> blobs;
@@ -47,7 +49,7 @@ struct ThreadCtx {
     {
         for (int d = 0; d < kMaxDev; d++) {
             DevCtx &c = dev[d];
-            if (!c.stream && !c.arena && !c.bounce && c.blobs.empty() && !c.pipe_stream[0]) continue;
+            if (!c.stream && !c.arena && !c.plane_stage && !c.bounce && c.blobs.empty() && !c.pipe_stream[0]) continue;
             if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
             cudaDeviceSynchronize();     // batched calls may have run on caller-supplied streams that still read our tables
             for (int s = 0; s < kPipeSlots; s++) {
@@ -56,6 +58,7 @@ struct ThreadCtx {
             }
             for (Blob &b : c.blobs) cudaFree(b.dptr);
             if (c.arena) cudaFree(c.arena);
+            if (c.plane_stage) cudaFree(c.plane_stage);
             if (c.bounce) cudaFreeHost(c.bounce);
             if (c.sleep_ev) cudaEventDestroy(c.sleep_ev);
             if (c.arena_ev) cudaEventDestroy(c.arena_ev);

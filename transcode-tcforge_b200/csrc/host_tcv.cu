@@ -35,7 +35,7 @@ void build_resize_table(int oldsize, int newsize, std::vector<int32_t> &src, std
 
 // Host frames for the frame-granular entry points.  These functions are written for device-resident planes; when the
 // caller's source and/or destination is host memory (unmodified libtcvideo callers hold host frame buffers) the planes go
-// through the thread's device arena: one upload of the batch, the operation on the device copies, one download, and the
+// through a per-thread device staging buffer: one upload of the batch, the operation on the device copies, one download, and the
 // call returns after the result has landed -- the same contract as the legacy per-frame ac_imgconvert path, but one
 // round trip per FRAME instead of one per ROW (tcv_deinterlace / tcv_resize call ac_average / ac_rescale per row).
 struct HostStage {
@@ -46,7 +46,12 @@ struct HostStage {
     size_t dsp = 0, ddp = 0, dp_host = 0, out_bytes = 0;
     int nf = 0;
 
-    HostStage(const uint8_t *src, size_t in_bytes, size_t spitch, uint8_t *dst, size_t outb, size_t dpitch, int nframes)
+    // preload_dest: the operation may leave destination bytes alone (alpha of YUV -> 32-bit RGB), so the host destination
+    // is uploaded first and survives the round trip
+    // device_in_place: when src == dst the operation may run in place on the device copy (flips); otherwise the device
+    // copy gets its own destination region and only the download lands on the shared host buffer
+    HostStage(const uint8_t *src, size_t in_bytes, size_t spitch, uint8_t *dst, size_t outb, size_t dpitch, int nframes,
+              bool preload_dest = false, bool device_in_place = true)
     {
         if (nframes <= 0) return;
         const bool src_host = !is_device_pointer(src);
@@ -58,12 +63,18 @@ struct HostStage {
         dest = dst; out_bytes = outb; nf = nframes;
         const size_t sp_host = spitch ? spitch : in_bytes;
         dp_host = dpitch ? dpitch : outb;
-        const bool in_place = static_cast<const void *>(src) == static_cast<const void *>(dst);
+        const bool in_place = device_in_place && static_cast<const void *>(src) == static_cast<const void *>(dst);
         dsp = src_host ? align_up(in_place && outb > in_bytes ? outb : in_bytes, 256) : sp_host;    // in place: room for the larger side
         ddp = in_place ? dsp : dst_host ? align_up(outb, 256) : dp_host;
         const size_t src_region = src_host ? dsp * (size_t)nframes : 0, dst_region = (dst_host && !in_place) ? ddp * (size_t)nframes : 0;
-        if (!ensure_arena(c, src_region + dst_region + 256) || !arena_acquire(c, c->stream)) { ok = false; return; }
-        uint8_t *as = c->arena, *ad = c->arena + src_region;
+        // (always used on the thread's own stream and every staged call ends with a sync: stream order is enough)
+        if (c->plane_stage_cap < src_region + dst_region + 256) {
+            if (c->plane_stage) { cudaStreamSynchronize(c->stream); cudaFree(c->plane_stage); c->plane_stage = nullptr; c->plane_stage_cap = 0; }
+            const size_t cap = align_up(src_region + dst_region + 256, 1u << 20);
+            if (!check(cudaMalloc(&c->plane_stage, cap), "cudaMalloc(plane staging)")) { ok = false; return; }
+            c->plane_stage_cap = cap;
+        }
+        uint8_t *as = c->plane_stage, *ad = c->plane_stage + src_region;
         if (src_host) {
             ok = check(cudaMemcpy2DAsync(as, dsp, src, sp_host, in_bytes, (size_t)nframes, cudaMemcpyHostToDevice, c->stream), "H2D planes");
             dsrc = as;
@@ -71,6 +82,8 @@ struct HostStage {
             dsrc = src;
         }
         ddst = in_place ? const_cast<uint8_t *>(dsrc) : dst_host ? ad : dst;
+        if (ok && preload_dest && dst_host && !in_place && outb)
+            ok = check(cudaMemcpy2DAsync(ad, ddp, dst, dp_host, outb, (size_t)nframes, cudaMemcpyHostToDevice, c->stream), "H2D dest planes");
     }
     acgpu_stream_t stream() const { return reinterpret_cast<acgpu_stream_t>(c->stream); }
     int finish(int launched)
@@ -261,6 +274,13 @@ int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, Imag
     if (nframes <= 0) return 1;
     cudaStream_t st = pick_stream(c, stream);
     const size_t sfb = frame_bytes(sf, width, height), dfb = frame_bytes(df, width, height);
+    {
+        // (src == dest on the host: the device copy converts into a separate region, no device-side temporary needed)
+        HostStage hs(src, sfb, spitch, dest, dfb, dpitch, nframes, /*preload_dest=*/src != dest, /*device_in_place=*/false);
+        if (hs.staged)
+            return hs.finish(hs.ok && acgpu_convert_batch(const_cast<uint8_t *>(hs.dsrc), hs.ddst, width, height, srcfmt, destfmt,
+                                                          hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
     if (srcfmt == destfmt) {
         if (src == dest) return 1;
         return check(cudaMemcpy2DAsync(dest, dpitch ? dpitch : dfb, src, spitch ? spitch : sfb, dfb, nframes,
