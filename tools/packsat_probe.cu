@@ -1,4 +1,5 @@
-// Probe: semantics of cvt.pack.sat.u8.s32.b32 and mad.wide.s32 on sm_100a (scratch, not part of the product).
+// Probe: semantics of cvt.pack.sat.u8.s32.b32 and mad.wide.s32 on sm_100a (profiling aid, not part of the product).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -o /tmp/packsat_probe tools/packsat_probe.cu && /tmp/packsat_probe
 #include <cstdio>
 #include <cstdint>
 __global__ void k(const int *a, const int *b, const unsigned *c, unsigned *d, long long *w, int n)
