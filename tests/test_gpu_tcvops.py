@@ -285,3 +285,34 @@ def test_host_frames_are_staged_once_per_call(ac, tcv, kind):
                 assert (gap == (0x21 if inplace else 0x55)).all(), (key, kind, "gap written")
         for k in keep:
             k.free()
+
+
+@pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160), (854, 480)])
+def test_size_independent_properties_at_full_sizes(ac, size):
+    """Relations that hold at any size, checked at BASELINE's frame sizes where the checker would take long:
+    grow-then-clip is the identity and the grown border is the black value; reduce by (1,1) is a copy; reduce by
+    (2,2) is the even pixels of the even rows; dropping the bottom field gives the even rows, which are also the even
+    rows of the interpolating deinterlacer; vertical flip twice is the identity."""
+    w, h = size
+    for bpp in (1, 3):
+        src = ck.splitmix_bytes(w * h * bpp, 17 + bpp)
+        f = src[None, :]
+        img = src.reshape(h, w, bpp)
+        gw, gh = w + 24, h + 10
+        _, grown = ac.plane_op_batch("clip", f, gw * gh * bpp, w, h, bpp, -8, -16, -4, -6, 99)
+        g = grown[0].reshape(gh, gw, bpp)
+        assert np.array_equal(g[4:4 + h, 8:8 + w], img)
+        assert (g[:4] == 99).all() and (g[4 + h:] == 99).all() and (g[:, :8] == 99).all() and (g[:, 8 + w:] == 99).all()
+        _, back = ac.plane_op_batch("clip", grown, w * h * bpp, gw, gh, bpp, 8, 16, 4, 6, 0)
+        assert np.array_equal(back[0], src)
+        _, same = ac.plane_op_batch("reduce", f, w * h * bpp, w, h, bpp, 1, 1)
+        assert np.array_equal(same[0], src)
+        _, half = ac.plane_op_batch("reduce", f, (w // 2) * (h // 2) * bpp, w, h, bpp, 2, 2)
+        assert np.array_equal(half[0].reshape(h // 2, w // 2, bpp), img[0:h - h % 2:2, 0:w - w % 2:2])
+        _, even = ac.plane_op_batch("deinterlace", f, w * (h // 2) * bpp, w, h, bpp, 3)
+        assert np.array_equal(even[0].reshape(h // 2, w, bpp), img[0:2 * (h // 2):2])
+        _, interp = ac.plane_op_batch("deinterlace", f, w * h * bpp, w, h, bpp, 0)
+        assert np.array_equal(interp[0].reshape(h, w, bpp)[0::2], img[0::2])
+        _, v = ac.plane_op_batch("flip_v", f, w * h * bpp, w, h, bpp)
+        _, vv = ac.plane_op_batch("flip_v", v, w * h * bpp, w, h, bpp)
+        assert np.array_equal(vv[0], src) and np.array_equal(v[0].reshape(h, w, bpp), img[::-1])
