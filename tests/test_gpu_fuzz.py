@@ -192,3 +192,38 @@ def test_fuzz_plane_operations(ac, chunk):
         assert np.array_equal(dsrc.download(), hs), what + ": source modified"
         dsrc.free()
         ddst.free()
+
+
+@pytest.mark.parametrize("chunk", range(3))
+def test_fuzz_legacy_host_calls(ac, chk, chunk):
+    """The unmodified ac_imgconvert(src planes, fmt, dest planes, fmt, w, h) call on pageable host memory: random pairs
+    and sizes, planes at arbitrary (unaligned) host addresses, canaries around every destination plane."""
+    rng = np.random.default_rng(4400 + chunk)
+    fmts = F.FORMATS_15
+    for case in range(60):
+        sf, df = fmts[int(rng.integers(0, len(fmts)))], fmts[int(rng.integers(0, len(fmts)))]
+        w, h = pick_size(rng, sf, df, bool(rng.integers(0, 2)))
+        ssz, dsz = F.plane_sizes(sf, w, h), F.plane_sizes(df, w, h)
+        soff, stot = layout(rng, ssz, False)
+        doff, dtot = layout(rng, dsz, False)
+        frame = ck.random_frame(sf, w, h, seed=int(rng.integers(0, 1 << 30)))
+        hs = np.full(stot + 64, 0x11, np.uint8)
+        o = 0
+        for p, s in enumerate(ssz):
+            hs[soff[p]: soff[p] + s] = frame[o:o + s]
+            o += s
+        keep = hs.copy()
+        hd = np.full(dtot + 64, CANARY, np.uint8)
+        sp = (C.c_void_p * 3)(*[hs.ctypes.data + soff[p] if p < len(ssz) else None for p in range(3)])
+        dp = (C.c_void_p * 3)(*[hd.ctypes.data + doff[p] if p < len(dsz) else None for p in range(3)])
+        ok = ac.lib.ac_imgconvert(sp, sf, dp, df, w, h)
+        what = f"chunk {chunk} case {case}: {F.NAMES[sf]}->{F.NAMES[df]} {w}x{h}"
+        assert ok == 1, (what, ac.last_error())
+        _, d = chk.convert(frame, sf, df, w, h, prefill=CANARY, pad=0)
+        want = np.full_like(hd, CANARY)
+        o = 0
+        for p, s in enumerate(dsz):
+            want[doff[p]: doff[p] + s] = d[o:o + s]
+            o += s
+        assert np.array_equal(hd, want), what
+        assert np.array_equal(hs, keep), what + ": source modified"
