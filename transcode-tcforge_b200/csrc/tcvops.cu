@@ -296,21 +296,28 @@ __global__ void __launch_bounds__(kThreads) k_lut(const uint8_t *src0, size_t sp
     const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
     uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
     const uint32_t nchunks = (nbytes + 15) / 16, stride = gridDim.x * blockDim.x;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
-        const uint32_t off = c * 16;
-        if (vec && off + 16 <= nbytes) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(src + off);
-            const uint32_t in[4] = {v.x, v.y, v.z, v.w};
-            uint32_t out[4];
+    auto map16 = [&](uint4 v) {
+        const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+        uint32_t out[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t a = s_t[in[k] & 0xFFu], b = s_t[(in[k] >> 8) & 0xFFu], cc = s_t[(in[k] >> 16) & 0xFFu], d = s_t[in[k] >> 24];
-                out[k] = __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(cc, d, 0x0040), 0x5410);
-            }
-            stg128(dst + off, make_uint4(out[0], out[1], out[2], out[3]));
-        } else {
-            for (uint32_t i = off; i < off + 16 && i < nbytes; i++) dst[i] = s_t[src[i]];
+        for (int k = 0; k < 4; k++) {
+            const uint32_t a = s_t[in[k] & 0xFFu], b = s_t[(in[k] >> 8) & 0xFFu], cc = s_t[(in[k] >> 16) & 0xFFu], d = s_t[in[k] >> 24];
+            out[k] = __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(cc, d, 0x0040), 0x5410);
         }
+        return make_uint4(out[0], out[1], out[2], out[3]);
+    };
+    // two chunks per trip: both loads are issued before either is used (one 16-byte load per thread in flight does not
+    // cover HBM latency)
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += 2 * stride) {
+        const uint32_t off0 = c * 16, c1 = c + stride, off1 = c1 * 16;
+        const bool whole0 = vec && off0 + 16 <= nbytes, has1 = c1 < nchunks, whole1 = has1 && vec && off1 + 16 <= nbytes;
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+        if (whole0) v0 = *reinterpret_cast<const uint4 *>(src + off0);
+        if (whole1) v1 = *reinterpret_cast<const uint4 *>(src + off1);
+        if (whole0) stg128(dst + off0, map16(v0));
+        else for (uint32_t i = off0; i < off0 + 16 && i < nbytes; i++) dst[i] = s_t[src[i]];
+        if (whole1) stg128(dst + off1, map16(v1));
+        else if (has1) for (uint32_t i = off1; i < off1 + 16 && i < nbytes; i++) dst[i] = s_t[src[i]];
     }
 }
 
