@@ -15,6 +15,20 @@
  * Every call acts on the calling thread's current device (acgpu_set_device; default 0, or
  * $ACGPU_DEVICE).  `stream` may be NULL = the calling thread's private stream.  Batched calls are
  * asynchronous with respect to the host; use acgpu_stream_sync() or events.
+ *
+ * Ordering: a batched call given HOST memory on either side runs its upload / kernels / download on the thread's
+ * private stream, ordered after everything queued so far on the stream the caller named, and returns when the result
+ * has landed.  The legacy aclib calls (ac_imgconvert, ac_average, ac_rescale, ac_memcpy) have no stream argument: with
+ * device pointers they order only against the thread's private stream -- synchronise other streams first.
+ * ac_memcpy treats every pointer as host memory until the process has called an acgpu_* function that can hand out or
+ * select device memory (acgpu_malloc, acgpu_set_device, acgpu_stream_create, any batched call): unmodified callers pay no
+ * driver query per copy.
+ * Pitches: a frame pitch of 0 means tightly packed frames; a pitch smaller than a frame is rejected when nframes > 1
+ * (acgpu_imgconvert_batch and acgpu_rowops_run take separate plane / row offsets and need explicit pitches).
+ * In place: src == dest is accepted where the reference's sequential result is well defined and equal to the out-of-place
+ * one -- flips, gamma, conversion (through a temporary, tcvideo.c:1044-1064), cropping clip, reduce, drop-field and
+ * interpolating deinterlace, shrinking resize -- and rejected elsewhere (growing clip, enlarging resize, linear blend,
+ * antialias); partially overlapping src / dest are always rejected (tcvideo.c:180 "src and dest do not overlap").
  */
 #ifndef ACGPU_H
 #define ACGPU_H
@@ -173,6 +187,57 @@ int acgpu_gamma_correct_batch(const uint8_t *src, uint8_t *dest, int width, int 
 /* tcv_antialias (tcvideo.c:886-980), weight tables as :1209-1224; src and dest must not overlap. */
 int acgpu_antialias_batch(const uint8_t *src, uint8_t *dest, int width, int height, int Bpp, double weight, double bias,
                           size_t src_frame_pitch, size_t dest_frame_pitch, int nframes, acgpu_stream_t stream);
+
+/* ---- frame chains: several operations per PCIe round trip -----------------------------------------------------------
+ * transcode applies a list of operations to every frame (do_process_frame, src/video_trans.c:192-426: clip, deinterlace,
+ * resize, clip, reduce, flip, mirror, -k, -K, gamma, antialias) and its filter wrappers convert yuv -> rgb -> filter -> yuv
+ * (filter/filter_ascii.c:367-373).  A chain runs such a list on the device copy of a frame: one upload, N kernels, one
+ * download.  Frames are whole images in transcode's layouts (tightly packed, YUV_INIT_PLANES); every stage other than
+ * CONVERT needs a YUV420P, YUV422P or RGB24 frame -- the layouts do_process_frame knows (video_trans.c:85-103); Y8 / GRAY8 pass
+ * as its default single 8-bit plane (video_trans.c:77-84; no -k / -K there) -- and treats its planes as the reference does: PROCESS_FRAME stages run on every plane with the chroma planes' divided sizes and
+ * arguments, the first-plane-only stages (-I 1/5, gamma, antialias) leave chroma alone.  Results are byte-identical to the
+ * same libtcvideo / ac_imgconvert calls made one after the other on the host. */
+enum {
+    ACGPU_CHAIN_CONVERT = 1,   /* tcv_convert (tcvideo.c:1001-1067): p[0] = destination ImageFormat, any of the 225 pairs   */
+    ACGPU_CHAIN_CLIP,          /* -j / -Y (video_trans.c:213-223, 327-337): p[0..3] = left, right, top, bottom in frame pixels
+                                  (negative grows the frame with black: 0 / chroma 128); multiples of the chroma subsampling */
+    ACGPU_CHAIN_DEINTERLACE,   /* -I (video_trans.c:227-279): p[0] = 1 interpolate, 5 linear blend (first plane), 4 drop field
+                                  (all planes, half height), 2 nothing (left to the encoder); 3 needs tcv_zoom: rejected       */
+    ACGPU_CHAIN_RESIZE,        /* -B / -X (video_trans.c:281-297): p[0] = resize_w, p[1] = resize_h in units of 8 pixels, rows first */
+    ACGPU_CHAIN_REDUCE,        /* -r (video_trans.c:341-345): p[0] = reduce_w, p[1] = reduce_h                                */
+    ACGPU_CHAIN_FLIP_V,        /* -z */
+    ACGPU_CHAIN_FLIP_H,        /* -l */
+    ACGPU_CHAIN_RGBSWAP,       /* -k (video_trans.c:349-366): R <-> B, or U <-> V planes                                      */
+    ACGPU_CHAIN_DECOLOR,       /* -K (video_trans.c:370-386): RGB24 -> GRAY8 -> RGB24, or chroma planes = 128                 */
+    ACGPU_CHAIN_GAMMA,         /* -G (video_trans.c:390-396): d[0] = gamma, first plane only                                  */
+    ACGPU_CHAIN_ANTIALIAS      /* -C (video_trans.c:400-421): d[0] = weight, d[1] = bias, first plane only                    */
+};
+typedef struct {
+    int32_t kind;      /* ACGPU_CHAIN_* */
+    int32_t p[5];
+    double  d[2];
+} acgpu_chain_op;
+
+/* Layout of the frames a chain produces (checks the whole list; 0 + acgpu_last_error() if a stage cannot apply). */
+int acgpu_chain_output(ImageFormat fmt, int width, int height, const acgpu_chain_op *ops, int nops,
+                       ImageFormat *out_fmt, int *out_width, int *out_height);
+/* Device-resident: `nframes` frames a fixed pitch apart (0 = tightly packed), src is not modified, src and dest must not
+ * overlap.  Intermediate frames live in the calling thread's temporary and the batch is walked in sub-batches small enough
+ * for them to stay in L2 between stages.  Asynchronous on `stream`. */
+int acgpu_chain_batch(const uint8_t *src, ImageFormat fmt, int width, int height, size_t src_frame_pitch,
+                      uint8_t *dest, size_t dest_frame_pitch, const acgpu_chain_op *ops, int nops, int nframes,
+                      acgpu_stream_t stream);
+/* Host frames, tightly packed one after the other (best: acgpu_host_alloc memory): chunks of frames go through a three-slot
+ * upload / chain / download pipeline; returns after everything has landed in dest_frames.  The _multi form cuts the run
+ * into one contiguous block per device like acgpu_imgconvert_frames_host_multi. */
+int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
+                            const acgpu_chain_op *ops, int nops, int nframes);
+int acgpu_chain_frames_host_multi(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
+                                  const acgpu_chain_op *ops, int nops, int nframes, int ndevices);
+
+/* Optional: stops the per-device host threads of the *_multi calls while the CUDA runtime is still alive.  Without it
+ * they are abandoned at process exit (never joined from a static destructor). */
+void acgpu_shutdown(void);
 
 #ifdef __cplusplus
 }

@@ -135,3 +135,35 @@ def test_product_never_touches_the_oracle():
             text = open(os.path.join(tools, f), errors="ignore").read()
             for needle in ("liboracle", "ac_oracle", "oracle_", "oracle/", "libac_ref", "libtcv_ref", "import checkers"):
                 assert needle not in text, f"tools/{f} references {needle}"
+
+
+def test_chain_planning_needs_no_device(ac):
+    """acgpu_chain_output walks a stage list on the host: geometry as do_process_frame computes it
+    (src/video_trans.c:213-345), rejections with a reason."""
+    import ctypes as C
+    F = pkg.F
+
+    def plan(fmt, w, h, stages):
+        ops = pkg.chain_ops(stages)
+        of, ow, oh = C.c_int(0), C.c_int(0), C.c_int(0)
+        ok = ac.lib.acgpu_chain_output(fmt, w, h, ops, len(stages), C.byref(of), C.byref(ow), C.byref(oh))
+        return ok, of.value, ow.value, oh.value
+
+    assert plan(F.IMG_YUV420P, 3840, 2160, [(pkg.CHAIN_CONVERT, F.IMG_RGB24), (pkg.CHAIN_CONVERT, F.IMG_YUV422P)]) == (1, F.IMG_YUV422P, 3840, 2160)
+    assert plan(F.IMG_YUV420P, 720, 576, [(pkg.CHAIN_CLIP, 8, 8, 16, 16), (pkg.CHAIN_DEINTERLACE, 1), (pkg.CHAIN_RESIZE, -6, -4),
+                                          (pkg.CHAIN_FLIP_V,), (pkg.CHAIN_GAMMA, 0.8)]) == (1, F.IMG_YUV420P, 656, 512)
+    assert plan(F.IMG_YUV422P, 352, 288, [(pkg.CHAIN_DEINTERLACE, 4), (pkg.CHAIN_RESIZE, 4, 2), (pkg.CHAIN_CLIP, -16, -16, -8, -8),
+                                          (pkg.CHAIN_REDUCE, 2, 2)]) == (1, F.IMG_YUV422P, 208, 88)
+    assert plan(F.IMG_RGB24, 64, 32, []) == (1, F.IMG_RGB24, 64, 32)
+    for fmt, stages, why in [
+        (F.IMG_YUY2, [(pkg.CHAIN_FLIP_V,)], "YUV420P, YUV422P, RGB24"),
+        (F.IMG_Y8, [(pkg.CHAIN_DECOLOR,)], "colour planes"),
+        (F.IMG_YUV420P, [(pkg.CHAIN_CLIP, 1, 0, 0, 0)], "multiples"),
+        (F.IMG_YUV420P, [(pkg.CHAIN_DEINTERLACE, 3)], "tcv_zoom"),
+        (F.IMG_RGB24, [(pkg.CHAIN_CLIP, 40, 40, 0, 0)], "no frame"),
+        (F.IMG_RGB24, [(pkg.CHAIN_REDUCE, 0, 1)], "reduce"),
+        (F.IMG_RGB24, [(pkg.CHAIN_CONVERT, 0x7777)], "unknown format"),
+        (F.IMG_RGB24, [(99,)], "unknown stage"),
+    ]:
+        ok, *_ = plan(fmt, 64, 32, stages)
+        assert ok == 0 and why in ac.last_error(), (stages, ac.last_error())

@@ -132,6 +132,24 @@ def test_config2_matrix_1080p(ac, chk, a, b):
         assert_same(got, want, f"1080p {F.NAMES[sf]}->{F.NAMES[df]}")
 
 
+# ---- every pair at full size: the grid-stride paths (block clamp, several trips per block, frame segments) that the
+# small all-pairs tests never reach (testsuite/test-imgconvert.c runs its matrix at one size only, 768x512) -------------
+@pytest.mark.parametrize("size", [(1920, 1080), (1280, 720)], ids=lambda s: f"{s[0]}x{s[1]}")
+@pytest.mark.parametrize("srcfmt", F.FORMATS_16, ids=lambda f: F.NAMES[f])
+def test_all_pairs_full_size(ac, chk, srcfmt, size):
+    w, h = size
+    nf = 2
+    frames = np.stack([ck.random_frame(srcfmt, w, h, seed=70 + i) for i in range(nf)])
+    for dstfmt in F.FORMATS_16:
+        dfb = F.frame_bytes(dstfmt, w, h)
+        got = ac.convert_batch(frames, srcfmt, dstfmt, w, h, dst_pitch=dfb + 256)
+        assert ac.lib.acgpu_last_kernel_tier() >= 2, "fell back to the generic tier"
+        for i in range(nf):
+            _, want = chk.convert(frames[i], srcfmt, dstfmt, w, h, pad=0)
+            assert_same(got[i, :dfb], want, f"{w}x{h} {F.NAMES[srcfmt]}->{F.NAMES[dstfmt]} frame {i}")
+        assert (got[:, dfb:] == 0x55).all(), "wrote into the inter-frame gap"
+
+
 def test_config1_pal_and_config4_uhd_round_trip(ac, chk):
     # config 1 size (PAL; chroma pitch 360 is not 16-byte aligned) and config 4 (UHD 420P->RGB24->422P)
     w, h = 720, 576

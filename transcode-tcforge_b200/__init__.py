@@ -43,6 +43,29 @@ class RowOp(C.Structure):
                 ("op", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+CHAIN_CONVERT, CHAIN_CLIP, CHAIN_DEINTERLACE, CHAIN_RESIZE, CHAIN_REDUCE, CHAIN_FLIP_V, CHAIN_FLIP_H, CHAIN_RGBSWAP, \
+    CHAIN_DECOLOR, CHAIN_GAMMA, CHAIN_ANTIALIAS = range(1, 12)
+
+
+class ChainOp(C.Structure):
+    """include/acgpu.h acgpu_chain_op."""
+    _fields_ = [("kind", C.c_int32), ("p", C.c_int32 * 5), ("d", C.c_double * 2)]
+
+
+def chain_ops(stages):
+    """[(kind, ints..., floats...)] -> C array of acgpu_chain_op; ints fill p[], floats fill d[]."""
+    arr = (ChainOp * max(len(stages), 1))()
+    for i, st in enumerate(stages):
+        arr[i].kind = st[0]
+        ints = [v for v in st[1:] if isinstance(v, (int, np.integer))]
+        flts = [v for v in st[1:] if isinstance(v, float)]
+        for j, v in enumerate(ints):
+            arr[i].p[j] = int(v)
+        for j, v in enumerate(flts):
+            arr[i].d[j] = float(v)
+    return arr
+
+
 class AcGpuError(RuntimeError):
     pass
 
@@ -61,6 +84,7 @@ ABI_SYMBOLS = [
     "acgpu_convert_batch", "acgpu_decolor_rgb24_batch",
     "acgpu_clip_batch", "acgpu_reduce_batch", "acgpu_flip_v_batch", "acgpu_flip_h_batch",
     "acgpu_gamma_correct_batch", "acgpu_antialias_batch",
+    "acgpu_chain_output", "acgpu_chain_batch", "acgpu_chain_frames_host", "acgpu_chain_frames_host_multi", "acgpu_shutdown",
 ]
 
 
@@ -103,6 +127,11 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "acgpu_flip_h_batch": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, vp]),
         "acgpu_gamma_correct_batch": (i32, [vp, vp, i32, i32, i32, C.c_double, sz, sz, i32, vp]),
         "acgpu_antialias_batch": (i32, [vp, vp, i32, i32, i32, C.c_double, C.c_double, sz, sz, i32, vp]),
+        "acgpu_chain_output": (i32, [i32, i32, i32, C.POINTER(ChainOp), i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "acgpu_chain_batch": (i32, [vp, i32, i32, i32, sz, vp, sz, C.POINTER(ChainOp), i32, i32, vp]),
+        "acgpu_chain_frames_host": (i32, [vp, i32, i32, i32, vp, C.POINTER(ChainOp), i32, i32]),
+        "acgpu_chain_frames_host_multi": (i32, [vp, i32, i32, i32, vp, C.POINTER(ChainOp), i32, i32, i32]),
+        "acgpu_shutdown": (None, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

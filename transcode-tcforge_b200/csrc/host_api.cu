@@ -39,6 +39,12 @@ namespace {
 
 std::atomic<int> g_initialised{0};
 std::atomic<int> g_sm_count{0};
+// Set by the first acgpu_* call that can put device memory into a caller's hands (acgpu_malloc, acgpu_set_device,
+// acgpu_stream_create, any batched entry point).  Until then every pointer handed to ac_memcpy is host memory.
+std::atomic<bool> g_cuda_aware{false};
+// Set at process exit: thread-local and static destructors then leave CUDA alone (the runtime may already be gone).
+std::atomic<bool> g_exiting{false};
+struct ExitHook { ExitHook() { atexit([] { g_exiting.store(true); }); } } g_exit_hook;
 
 int default_device()
 {
@@ -63,6 +69,9 @@ bool bind_device()
 }
 
 }  // namespace
+
+bool process_exiting() { return g_exiting.load(); }
+
 DevCtx *ctx()
 {
     if (!bind_device()) return nullptr;
@@ -71,10 +80,24 @@ DevCtx *ctx()
         return nullptr;
     return c;
 }
-namespace {
 
-}  // namespace
-cudaStream_t pick_stream(DevCtx *c, acgpu_stream_t s) { return s ? reinterpret_cast<cudaStream_t>(s) : c->stream; }
+cudaStream_t pick_stream(DevCtx *c, acgpu_stream_t s)
+{
+    g_cuda_aware.store(true, std::memory_order_relaxed);     // only acgpu_* entry points name streams
+    return s ? reinterpret_cast<cudaStream_t>(s) : c->stream;
+}
+
+// Staged (host-pointer) work runs on the thread's private stream.  When the caller named another stream, device data it
+// hands over may still be in flight there: the private stream is ordered after everything queued on the caller's
+// stream so far.
+bool order_after(DevCtx *c, acgpu_stream_t caller)
+{
+    cudaStream_t cs = reinterpret_cast<cudaStream_t>(caller);
+    if (!cs || cs == c->stream) return true;
+    if (!c->order_ev && !check(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming), "cudaEventCreate")) return false;
+    return check(cudaEventRecord(c->order_ev, cs), "order record") && check(cudaStreamWaitEvent(c->stream, c->order_ev, 0), "order wait");
+}
+
 namespace {
 
 [[noreturn]] void fatal(const char *what)
@@ -102,7 +125,9 @@ PtrKind classify(const void *p)
 }
 
 }  // namespace
+
 bool is_device_pointer(const void *p) { return classify(p) == PK_DEVICE; }
+
 bool ensure_arena(DevCtx *c, size_t bytes)
 {
     if (bytes <= c->arena_cap) return true;
@@ -117,24 +142,22 @@ bool ensure_arena(DevCtx *c, size_t bytes)
     c->arena_cap = cap;
     return true;
 }
-namespace {
 
 // The arena is one buffer per (thread, device) but the batched entry points run on whatever stream the caller names.
 // A use of the arena on stream B must not start before an earlier, still unfinished use on stream A is over:
 // arena_acquire makes B wait for the event the previous user recorded, arena_release records it.
-}  // namespace
 bool arena_acquire(DevCtx *c, cudaStream_t st)
 {
     if (!c->arena_ev) return true;
     return check(cudaStreamWaitEvent(st, c->arena_ev, 0), "arena wait");
 }
-namespace {
-}  // namespace
+
 bool arena_release(DevCtx *c, cudaStream_t st)
 {
     if (!c->arena_ev && !check(cudaEventCreateWithFlags(&c->arena_ev, cudaEventDisableTiming), "cudaEventCreate")) return false;
     return check(cudaEventRecord(c->arena_ev, st), "arena record");
 }
+
 namespace {
 
 bool ensure_bounce(DevCtx *c, size_t bytes)
@@ -254,8 +277,20 @@ bool convert_one(Image si, int sfmt, Image di, int dfmt, int w, int h)
     int snp, dnp;
     plane_sizes(sfmt, w, h, ssz, &snp);
     plane_sizes(dfmt, w, h, dsz, &dnp);
-    const bool src_host = classify(si.p[0]) != PK_DEVICE;
-    const bool dst_host = classify(di.p[0]) != PK_DEVICE;
+    // one driver query per plane: every plane of an image must live on the same side (a host/device mix would be staged
+    // wrongly), and the pageable / page-locked distinction decides whether the bounce buffer is used
+    PtrKind sk = classify(si.p[0]), dk = classify(di.p[0]);
+    for (int p = 1; p < snp; p++) {
+        const PtrKind k = classify(si.p[p]);
+        if ((k == PK_DEVICE) != (sk == PK_DEVICE)) { set_error("ac_imgconvert: source planes mix host and device memory"); return false; }
+        if (k == PK_HOST) sk = sk == PK_DEVICE ? sk : PK_HOST;      // one pageable plane makes the image pageable
+    }
+    for (int p = 1; p < dnp; p++) {
+        const PtrKind k = classify(di.p[p]);
+        if ((k == PK_DEVICE) != (dk == PK_DEVICE)) { set_error("ac_imgconvert: destination planes mix host and device memory"); return false; }
+        if (k == PK_HOST) dk = dk == PK_DEVICE ? dk : PK_HOST;
+    }
+    const bool src_host = sk != PK_DEVICE, dst_host = dk != PK_DEVICE;
 
     size_t need = 0, soff[3] = {0, 0, 0}, doff[3] = {0, 0, 0};
     if (src_host)
@@ -269,8 +304,7 @@ bool convert_one(Image si, int sfmt, Image di, int dfmt, int w, int h)
     a.src = si; a.dst = di;
     a.src.pitch = a.dst.pitch = 0;
     // pageable caller memory: through the pinned bounce buffer when other threads are converting too
-    const bool src_pageable = src_host && classify(si.p[0]) == PK_HOST;
-    const bool dst_pageable = dst_host && classify(di.p[0]) == PK_HOST;
+    const bool src_pageable = sk == PK_HOST, dst_pageable = dk == PK_HOST;
     struct Busy {
         bool on;
         int  others;
@@ -328,6 +362,7 @@ uint64_t fnv1a(const void *p, size_t n)
 // Returns a device copy of a small host table, cached per (thread, device) by content.
 constexpr size_t kBlobCacheEntries = 64;
 }  // namespace
+
 void *device_blob(DevCtx *c, const void *host, size_t bytes, cudaStream_t st)
 {
     // The list is kept in least-recently-used order: a hit moves to the back, a full cache drops its OLDER HALF.  One API
@@ -364,6 +399,7 @@ void *device_blob(DevCtx *c, const void *host, size_t bytes, cudaStream_t st)
     c->blobs.push_back(std::move(nb));
     return d;
 }
+
 namespace {
 
 bool device_usable(int *sms)
@@ -509,6 +545,10 @@ void *ac_memcpy(void *dest, const void *src, size_t size)
     // aclib/memcpy.c:16-25 is memmove (ascending copy guarantee, ac.h:80-82).  It is not pixel math, so
     // host buffers stay on the host; device buffers are copied on the device.
     if (size == 0 || dest == src) return dest;
+    // libtcvideo calls this once per ROW (tcvideo.c:229-246, 706-715): an unmodified caller -- one that never called an
+    // acgpu_* entry point and so cannot hold device memory -- pays no driver query per copy.
+    if (!g_cuda_aware.load(std::memory_order_relaxed)) return memmove(dest, src, size);
+    if (!bind_device()) fatal("ac_memcpy");                  // the query below would otherwise bind this thread to device 0
     const PtrKind kd = classify(dest), ks = classify(src);
     if (kd != PK_DEVICE && ks != PK_DEVICE) return memmove(dest, src, size);
     DevCtx *c = ctx();
@@ -596,6 +636,7 @@ int acgpu_device_count(void)
 
 int acgpu_set_device(int ordinal)
 {
+    g_cuda_aware.store(true, std::memory_order_relaxed);
     if (ordinal < 0 || ordinal >= kMaxDev || ordinal >= acgpu_device_count()) {
         set_error("acgpu_set_device: no device %d", ordinal);
         return 0;
@@ -618,6 +659,7 @@ uint64_t acgpu_launch_count(int reset)
 
 void *acgpu_malloc(size_t bytes)
 {
+    g_cuda_aware.store(true, std::memory_order_relaxed);
     void *p = nullptr;
     if (!bind_device() || !check(cudaMalloc(&p, bytes ? bytes : 1), "acgpu_malloc")) return nullptr;
     return p;
@@ -651,6 +693,7 @@ int acgpu_memset(void *dptr, int value, size_t bytes, acgpu_stream_t st)
 
 acgpu_stream_t acgpu_stream_create(void)
 {
+    g_cuda_aware.store(true, std::memory_order_relaxed);
     cudaStream_t s = nullptr;
     if (!bind_device() || !check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "acgpu_stream_create")) return nullptr;
     return reinterpret_cast<acgpu_stream_t>(s);
@@ -703,6 +746,11 @@ int acgpu_imgconvert_batch(uint8_t *const *src, ImageFormat srcfmt, size_t src_f
         return 0;
     }
     if (width <= 0 || height <= 0 || nframes <= 0) return 1;
+    if (nframes > 1 && (src_frame_pitch == 0 || dest_frame_pitch == 0)) {
+        // planes are separate pointers here, so "tightly packed" has no single meaning: a batch needs explicit pitches
+        set_error("acgpu_imgconvert_batch: frame pitch 0 with %d frames", nframes);
+        return 0;
+    }
     a.srcfmt = sfmt; a.dstfmt = dfmt; a.w = width; a.h = height;
     a.src.pitch = src_frame_pitch; a.dst.pitch = dest_frame_pitch;
     a.stream = pick_stream(c, stream);
@@ -763,93 +811,24 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
     return 1;
 }
 
-// Frames are independent: a run of host frames is cut into contiguous blocks, one per device, and every
-// block goes through that device's own pipeline on its own host thread.  No exchange between devices, no collective.
-// The per-device host threads are long-lived (created on first use, one per device, parked on a condition variable):
-// their streams, pipeline buffers and device contexts persist from call to call.
-}  // extern "C"
-
-namespace acgpu {
-namespace {
-
-struct DeviceWorker {
-    std::thread th;
-    std::mutex m;
-    std::condition_variable cv;
-    std::function<void()> job;
-    bool pending = false, quit = false;
-
-    DeviceWorker()
-    {
-        th = std::thread([this] {
-            std::unique_lock<std::mutex> lk(m);
-            for (;;) {
-                cv.wait(lk, [this] { return pending || quit; });
-                if (quit) return;
-                lk.unlock();
-                job();
-                lk.lock();
-                pending = false;
-                cv.notify_all();
-            }
-        });
-    }
-    void submit(std::function<void()> f)
-    {
-        std::lock_guard<std::mutex> lk(m);
-        job = std::move(f);
-        pending = true;
-        cv.notify_all();
-    }
-    void wait()
-    {
-        std::unique_lock<std::mutex> lk(m);
-        cv.wait(lk, [this] { return !pending; });
-    }
-    ~DeviceWorker()
-    {
-        { std::lock_guard<std::mutex> lk(m); quit = true; cv.notify_all(); }
-        if (th.joinable()) th.join();
-    }
-};
-
-std::mutex g_multi_mutex;                                     // one multi-device call at a time
-std::unique_ptr<DeviceWorker> g_workers[kMaxDev];
-
-}  // namespace
-}  // namespace acgpu
-
-extern "C" {
-
 int acgpu_imgconvert_frames_host_multi(const uint8_t *src_frames, ImageFormat srcfmt, uint8_t *dest_frames,
                                        ImageFormat destfmt, int width, int height, int nframes, int ndevices)
 {
-    int visible = 0;
-    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) { cudaGetLastError(); set_error("no CUDA device"); return 0; }
-    if (ndevices <= 0) ndevices = visible;
-    if (ndevices > visible || ndevices > kMaxDev) { set_error("acgpu_imgconvert_frames_host_multi: %d devices requested, %d visible", ndevices, visible); return 0; }
     const int sf = srcfmt == IMG_YV12 ? IMG_YUV420P : (int)srcfmt, df = destfmt == IMG_YV12 ? IMG_YUV420P : (int)destfmt;
     if (describe(sf).kind == K_NONE || describe(df).kind == K_NONE) { set_error("unknown format pair"); return 0; }
     if (width <= 0 || height <= 0 || nframes <= 0) return 1;
-    if (ndevices > nframes) ndevices = nframes;
     const size_t sfb = frame_bytes(sf, width, height), dfb = frame_bytes(df, width, height);
-    std::lock_guard<std::mutex> call(g_multi_mutex);
-    std::vector<int> ok((size_t)ndevices, 0);
-    std::vector<std::string> why((size_t)ndevices);
-    for (int d = 0; d < ndevices; d++) {
-        if (!g_workers[d]) g_workers[d].reset(new DeviceWorker());
-        const int f0 = (int)((int64_t)nframes * d / ndevices), f1 = (int)((int64_t)nframes * (d + 1) / ndevices);
-        g_workers[d]->submit([=, &ok, &why] {
-            ok[(size_t)d] = acgpu_set_device(d)
-                         && acgpu_imgconvert_frames_host(src_frames + (size_t)f0 * sfb, srcfmt, dest_frames + (size_t)f0 * dfb, destfmt,
-                                                         width, height, f1 - f0);
-            if (!ok[(size_t)d]) why[(size_t)d] = tls.err;
-        });
-    }
-    for (int d = 0; d < ndevices; d++) g_workers[d]->wait();
-    for (int d = 0; d < ndevices; d++)
-        if (!ok[(size_t)d]) { set_error("device %d: %s", d, why[(size_t)d].c_str()); return 0; }
-    return 1;
+    return run_on_devices("acgpu_imgconvert_frames_host_multi", ndevices, nframes, [=](int, int f0, int f1) {
+        return acgpu_imgconvert_frames_host(src_frames + (size_t)f0 * sfb, srcfmt, dest_frames + (size_t)f0 * dfb, destfmt,
+                                            width, height, f1 - f0) == 1;
+    });
+}
+
+void acgpu_shutdown(void)
+{
+    // Stops the per-device host threads of the *_multi calls (each gives its streams and buffers back as it exits) while
+    // the CUDA runtime is still alive.  Optional: without it they are simply abandoned at process exit.
+    stop_device_workers();
 }
 
 // ---- row operations -----------------------------------------------------------------------------------
@@ -860,6 +839,7 @@ int acgpu_rowops_run(const uint8_t *src, size_t spitch, uint8_t *dest, size_t dp
     if (!c) return 0;
     if (nops <= 0 || row_bytes <= 0 || nframes <= 0) return 1;
     if (!ops) { set_error("acgpu_rowops_run: null op list"); return 0; }
+    if (nframes > 1 && (spitch == 0 || dpitch == 0)) { set_error("acgpu_rowops_run: frame pitch 0 with %d frames", nframes); return 0; }
     cudaStream_t st = pick_stream(c, stream);
     bool al = true;
     for (int i = 0; i < nops && al; i++) {

@@ -6,6 +6,7 @@
 
 #include "acgpu_internal.h"
 
+#include <functional>
 #include <vector>
 
 namespace acgpu {
@@ -25,6 +26,7 @@ struct DevCtx {
     uint8_t *arena = nullptr;            // device staging for the legacy host-pointer calls
     size_t   arena_cap = 0;
     cudaEvent_t arena_ev = nullptr;      // recorded after the last asynchronous use of the arena (see arena_acquire)
+    cudaEvent_t order_ev = nullptr;      // orders the private stream after a caller-named stream (see order_after)
     uint8_t *plane_stage = nullptr;      // device copies of HOST planes handed to the frame-granular entry points (its own
     size_t   plane_stage_cap = 0;        // buffer: those entry points may use the arena as their temporary meanwhile)
     uint8_t *bounce = nullptr;           // pinned host mirror of the arena (pageable caller buffers go through it)
@@ -35,6 +37,8 @@ struct DevCtx {
     size_t   pipe_cap[kPipeSlots] = {0, 0, 0};
 };
 
+bool process_exiting();      // true once exit() has begun: destructors then leave CUDA alone
+
 struct ThreadCtx {
     int      device = -1;
     DevCtx   dev[kMaxDev];
@@ -42,11 +46,13 @@ struct ThreadCtx {
     uint64_t launches = 0;
     int      last_tier = 0;
     int      force_tier = 0;
+    int      device_only = 0;    // > 0 while a chain runs: every pointer handed to the entry points is device memory
 
     // A caller thread that exits gives its stream, staging buffers and cached tables back.  Best effort: at process
     // exit the CUDA runtime may already be gone, in which case these calls fail harmlessly.
     ~ThreadCtx()
     {
+        if (process_exiting()) return;
         for (int d = 0; d < kMaxDev; d++) {
             DevCtx &c = dev[d];
             if (!c.stream && !c.arena && !c.plane_stage && !c.bounce && c.blobs.empty() && !c.pipe_stream[0]) continue;
@@ -62,6 +68,7 @@ struct ThreadCtx {
             if (c.bounce) cudaFreeHost(c.bounce);
             if (c.sleep_ev) cudaEventDestroy(c.sleep_ev);
             if (c.arena_ev) cudaEventDestroy(c.arena_ev);
+            if (c.order_ev) cudaEventDestroy(c.order_ev);
             if (c.stream) cudaStreamDestroy(c.stream);
             cudaGetLastError();
         }
@@ -72,11 +79,16 @@ extern thread_local ThreadCtx tls;
 
 DevCtx      *ctx();                                            // binds the thread's device, creates its stream on first use
 cudaStream_t pick_stream(DevCtx *c, acgpu_stream_t s);         // the caller's stream, or the thread's own
+bool  order_after(DevCtx *c, acgpu_stream_t caller);           // private stream waits for what the caller's stream holds so far
 bool  is_device_pointer(const void *p);                        // device / managed memory (else pageable or page-locked host)
 bool  ensure_arena(DevCtx *c, size_t bytes);
 bool  arena_acquire(DevCtx *c, cudaStream_t st);               // orders uses of the arena on different streams
 bool  arena_release(DevCtx *c, cudaStream_t st);
 void *device_blob(DevCtx *c, const void *host, size_t bytes, cudaStream_t st);   // cached device copy of a small host table
+
+// one long-lived host thread per device; job(device, first_frame, end_frame) runs there with the device selected (host_chain.cu)
+int   run_on_devices(const char *who, int ndevices, int nframes, const std::function<bool(int, int, int)> &job);
+void  stop_device_workers();
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -51,15 +51,18 @@ struct HostStage {
     // device_in_place: when src == dst the operation may run in place on the device copy (flips); otherwise the device
     // copy gets its own destination region and only the download lands on the shared host buffer
     HostStage(const uint8_t *src, size_t in_bytes, size_t spitch, uint8_t *dst, size_t outb, size_t dpitch, int nframes,
-              bool preload_dest = false, bool device_in_place = true)
+              acgpu_stream_t caller_stream, bool preload_dest = false, bool device_in_place = true)
     {
-        if (nframes <= 0) return;
+        if (nframes <= 0 || tls.device_only > 0) return;
         const bool src_host = !is_device_pointer(src);
-        dst_host = !is_device_pointer(dst);
+        dst_host = src == dst ? src_host : !is_device_pointer(dst);
         if (!src_host && !dst_host) return;
         staged = true;
         c = ctx();
         if (!c) { ok = false; return; }
+        // the staged sequence runs on the thread's private stream: a device-resident side may still be in flight on the
+        // stream the caller named
+        if (!order_after(c, caller_stream)) { ok = false; return; }
         dest = dst; out_bytes = outb; nf = nframes;
         const size_t sp_host = spitch ? spitch : in_bytes;
         dp_host = dpitch ? dpitch : outb;
@@ -96,6 +99,43 @@ struct HostStage {
     }
 };
 
+// One pitch rule for every entry point: 0 means tightly packed frames, and consecutive frames must not overlap.
+bool norm_pitch(const char *who, size_t *pitch, size_t frame_bytes, int nframes)
+{
+    if (*pitch == 0) *pitch = frame_bytes;
+    if (nframes > 1 && *pitch < frame_bytes) {
+        set_error("%s: frame pitch %zu is smaller than a frame (%zu bytes)", who, *pitch, frame_bytes);
+        return false;
+    }
+    return true;
+}
+
+// src/dest relation over the whole batch: 0 = disjoint, 1 = the same buffer (src == dest), -1 = partial overlap (rejected;
+// the reference's precondition is "src and dest do not overlap" unless they are equal, tcvideo.c:180).
+int alias_state(const char *who, const uint8_t *src, size_t spitch, size_t inb, const uint8_t *dst, size_t dpitch, size_t outb, int nframes)
+{
+    if (src == dst) return 1;
+    const size_t sspan = spitch * (size_t)(nframes - 1) + inb, dspan = dpitch * (size_t)(nframes - 1) + outb;
+    if (src < dst + dspan && dst < src + sspan) {
+        set_error("%s: src and dest overlap", who);
+        return -1;
+    }
+    return 0;
+}
+
+// src == dest on the device for an operation whose rows read other rows: the result is produced in the thread's temporary and
+// copied back, which equals the reference's sequential in-place result whenever every destination byte lies at or before
+// the source bytes it depends on (the callers check that; other in-place uses are rejected).
+template <class Op>
+int through_temp(DevCtx *c, cudaStream_t st, uint8_t *dest, size_t dpitch, size_t outb, int nframes, Op op)
+{
+    const size_t tp = align_up(outb, 256);
+    if (!ensure_arena(c, tp * (size_t)nframes) || !arena_acquire(c, st)) return 0;
+    if (!op(c->arena, tp)) return 0;
+    return check(cudaMemcpy2DAsync(dest, dpitch, c->arena, tp, outb, (size_t)nframes, cudaMemcpyDeviceToDevice, st), "in-place copy back")
+        && arena_release(c, st) ? 1 : 0;
+}
+
 }  // namespace
 }  // namespace acgpu
 
@@ -111,11 +151,27 @@ int acgpu_deinterlace_batch(const uint8_t *src, uint8_t *dest, int width, int he
     if (!src || !dest || width <= 0 || height <= 0 || (Bpp != 1 && Bpp != 3)) { set_error("acgpu_deinterlace_batch: invalid frame parameters"); return 0; }
     if (mode < ACGPU_DEINT_INTERPOLATE || mode > ACGPU_DEINT_DROP_FIELD_BOTTOM) { set_error("acgpu_deinterlace_batch: invalid mode %d", mode); return 0; }
     const int64_t Bpl = (int64_t)width * Bpp;
+    if (nframes <= 0) return 1;
+    const bool drop = mode == ACGPU_DEINT_DROP_FIELD_TOP || mode == ACGPU_DEINT_DROP_FIELD_BOTTOM;
+    const size_t inb = (size_t)Bpl * height, outb = (size_t)Bpl * (drop ? height / 2 : height);
+    if (!norm_pitch("acgpu_deinterlace_batch", &spitch, inb, nframes) || !norm_pitch("acgpu_deinterlace_batch", &dpitch, outb, nframes)) return 0;
+    const int alias = alias_state("acgpu_deinterlace_batch", src, spitch, inb, dest, dpitch, outb, nframes);
+    if (alias < 0) return 0;
+    if (alias && mode == ACGPU_DEINT_LINEAR_BLEND) {
+        // tcvideo.c:368-389 in place averages rows that were already blended: not a result worth reproducing
+        set_error("acgpu_deinterlace_batch: linear blend needs src != dest");
+        return 0;
+    }
     {
-        const bool drop = mode == ACGPU_DEINT_DROP_FIELD_TOP || mode == ACGPU_DEINT_DROP_FIELD_BOTTOM;
-        HostStage hs(src, (size_t)Bpl * height, spitch, dest, (size_t)Bpl * (drop ? height / 2 : height), dpitch, nframes);
+        HostStage hs(src, inb, spitch, dest, outb, dpitch, nframes, stream, false, /*device_in_place=*/false);
         if (hs.staged)
             return hs.finish(hs.ok && acgpu_deinterlace_batch(hs.dsrc, hs.ddst, width, height, Bpp, mode, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
+    if (alias) {    // interpolate / drop field in place: every row depends on rows at or after itself (tcvideo.c:326-364)
+        DevCtx *c = ctx();
+        if (!c) return 0;
+        return through_temp(c, pick_stream(c, stream), dest, dpitch, outb, nframes, [&](uint8_t *t, size_t tp) {
+            return acgpu_deinterlace_batch(src, t, width, height, Bpp, mode, spitch, tp, nframes, stream) == 1; });
     }
     if (mode == ACGPU_DEINT_DROP_FIELD_TOP || mode == ACGPU_DEINT_DROP_FIELD_BOTTOM) {
         // tcvideo.c:326-338: keep every other line, starting at line 1 when the top field is dropped
@@ -159,21 +215,41 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     auto ok_scale = [](int s) { return s == 1 || s == 2 || s == 4 || s == 8; };
     if (!ok_scale(scale_w) || !ok_scale(scale_h)) { set_error("acgpu_resize_batch: invalid scale parameters"); return 0; }
     if (width % scale_w != 0 || height % scale_h != 0) { set_error("acgpu_resize_batch: scale does not divide the frame"); return 0; }
-    if (resize_w && resize_h) { set_error("acgpu_resize_batch: only one of resize_w / resize_h may be non-zero"); return 0; }
     const int new_w = width + resize_w * scale_w, new_h = height + resize_h * scale_h;
     if (new_w <= 0 || new_h <= 0) { set_error("acgpu_resize_batch: resulting size is not positive"); return 0; }
+    if (resize_w && resize_h && new_h > height) {
+        // tcvideo.c:459-512 with both set: the horizontal pass reads rows 0..new_h-1 of SRC (not the vertically resized
+        // rows) and overwrites whatever the vertical pass left, so the result is defined only while those rows exist
+        set_error("acgpu_resize_batch: resize_w and resize_h both set with a taller result reads past the source frame");
+        return 0;
+    }
+    if (nframes <= 0) return 1;
+    const size_t inb = (size_t)width * height * Bpp, outb = (size_t)new_w * new_h * Bpp;
+    if (!norm_pitch("acgpu_resize_batch", &spitch, inb, nframes) || !norm_pitch("acgpu_resize_batch", &dpitch, outb, nframes)) return 0;
+    const int alias = alias_state("acgpu_resize_batch", src, spitch, inb, dest, dpitch, outb, nframes);
+    if (alias < 0) return 0;
+    if (alias && (resize_w > 0 || resize_h > 0 || (resize_w && resize_h))) {
+        set_error("acgpu_resize_batch: enlarging in place would read bytes already overwritten; use src != dest");
+        return 0;
+    }
     {
-        HostStage hs(src, (size_t)width * height * Bpp, spitch, dest, (size_t)new_w * new_h * Bpp, dpitch, nframes);
+        HostStage hs(src, inb, spitch, dest, outb, dpitch, nframes, stream, false, /*device_in_place=*/false);
         if (hs.staged)
             return hs.finish(hs.ok && acgpu_resize_batch(hs.dsrc, hs.ddst, width, height, Bpp, resize_w, resize_h, scale_w, scale_h,
                                                          hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
+    if (alias && (resize_w || resize_h)) {   // shrinking in place: destination bytes never lie after the source bytes they read
+        DevCtx *c = ctx();
+        if (!c) return 0;
+        return through_temp(c, pick_stream(c, stream), dest, dpitch, outb, nframes, [&](uint8_t *t, size_t tp) {
+            return acgpu_resize_batch(src, t, width, height, Bpp, resize_w, resize_h, scale_w, scale_h, spitch, tp, nframes, stream) == 1; });
     }
     DevCtx *c = ctx();
     if (!c) return 0;
     cudaStream_t st = pick_stream(c, stream);
     std::vector<int32_t> ts;
     std::vector<uint32_t> w1, w2;
-    if (resize_h) {
+    if (resize_h && !resize_w) {
         const int64_t Bpl = (int64_t)width * Bpp;
         build_resize_table(height * 8 / scale_h, new_h * 8 / scale_h, ts, w1, w2);
         const int rows = new_h / scale_h;
@@ -194,7 +270,7 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     if (resize_w) {
         build_resize_table(width * 8 / scale_w, new_w * 8 / scale_w, ts, w1, w2);
         const int n = (int)ts.size();
-        const size_t sp_ = spitch ? spitch : (size_t)width * height * Bpp, dp_ = dpitch ? dpitch : (size_t)new_w * new_h * Bpp;
+        const size_t sp_ = spitch, dp_ = dpitch;
         if (resize_h_vectorisable(src, sp_, dest, dp_, width, new_w, Bpp)) {
             // per-row byte tables: source byte offset (first tap) and packed weights for every output byte of a row
             const int src_block = width / scale_w, dst_block = new_w / scale_w;
@@ -274,17 +350,19 @@ int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, Imag
     if (nframes <= 0) return 1;
     cudaStream_t st = pick_stream(c, stream);
     const size_t sfb = frame_bytes(sf, width, height), dfb = frame_bytes(df, width, height);
+    if (!norm_pitch("acgpu_convert_batch", &spitch, sfb, nframes) || !norm_pitch("acgpu_convert_batch", &dpitch, dfb, nframes)) return 0;
+    if (src == dest && nframes > 1 && spitch != dpitch) { set_error("acgpu_convert_batch: in place needs one pitch"); return 0; }
+    if (alias_state("acgpu_convert_batch", src, spitch, sfb, dest, dpitch, dfb, nframes) < 0) return 0;
     {
         // (src == dest on the host: the device copy converts into a separate region, no device-side temporary needed)
-        HostStage hs(src, sfb, spitch, dest, dfb, dpitch, nframes, /*preload_dest=*/src != dest, /*device_in_place=*/false);
+        HostStage hs(src, sfb, spitch, dest, dfb, dpitch, nframes, stream, /*preload_dest=*/src != dest, /*device_in_place=*/false);
         if (hs.staged)
             return hs.finish(hs.ok && acgpu_convert_batch(const_cast<uint8_t *>(hs.dsrc), hs.ddst, width, height, srcfmt, destfmt,
                                                           hs.dsp, hs.ddp, nframes, hs.stream()));
     }
     if (srcfmt == destfmt) {
         if (src == dest) return 1;
-        return check(cudaMemcpy2DAsync(dest, dpitch ? dpitch : dfb, src, spitch ? spitch : sfb, dfb, nframes,
-                                       cudaMemcpyDeviceToDevice, st), "acgpu_convert_batch copy") ? 1 : 0;
+        return check(cudaMemcpy2DAsync(dest, dpitch, src, spitch, dfb, nframes, cudaMemcpyDeviceToDevice, st), "acgpu_convert_batch copy") ? 1 : 0;
     }
     uint8_t *real = dest;
     size_t rpitch = dpitch;
@@ -298,7 +376,7 @@ int acgpu_convert_batch(uint8_t *src, uint8_t *dest, int width, int height, Imag
     dp[0] = real; dp[1] = real + (size_t)width * height; dp[2] = dp[1] + chroma_plane_bytes(df, width, height);
     if (!acgpu_imgconvert_batch(sp, srcfmt, spitch, dp, destfmt, rpitch, width, height, nframes, stream)) return 0;
     if (src == dest)
-        return check(cudaMemcpy2DAsync(dest, dpitch ? dpitch : dfb, real, rpitch, dfb, nframes, cudaMemcpyDeviceToDevice, st),
+        return check(cudaMemcpy2DAsync(dest, dpitch, real, rpitch, dfb, nframes, cudaMemcpyDeviceToDevice, st),
                      "acgpu_convert_batch copy back") && arena_release(c, st) ? 1 : 0;
     return 1;
 }
@@ -311,7 +389,8 @@ int acgpu_decolor_rgb24_batch(uint8_t *frames, int width, int height, size_t pit
     if (nframes <= 0) return 1;
     {
         const size_t fb = (size_t)width * height * 3;
-        HostStage hs(frames, fb, pitch, frames, fb, pitch, nframes);
+        if (!norm_pitch("acgpu_decolor_rgb24_batch", &pitch, fb, nframes)) return 0;
+        HostStage hs(frames, fb, pitch, frames, fb, pitch, nframes, stream);
         if (hs.staged) return hs.finish(hs.ok && acgpu_decolor_rgb24_batch(hs.ddst, width, height, hs.ddp, nframes, hs.stream()));
     }
     cudaStream_t st = pick_stream(c, stream);
@@ -356,12 +435,23 @@ int acgpu_clip_batch(const uint8_t *src, uint8_t *dest, int width, int height, i
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    const size_t inb = (size_t)width * height * Bpp, outb = (size_t)(new_w * new_h * Bpp);
+    if (!norm_pitch("acgpu_clip_batch", &spitch, inb, nframes) || !norm_pitch("acgpu_clip_batch", &dpitch, outb, nframes)) return 0;
+    const int alias = alias_state("acgpu_clip_batch", src, spitch, inb, dest, dpitch, outb, nframes);
+    if (alias < 0) return 0;
+    if (alias && (clip_left < 0 || clip_right < 0 || clip_top < 0 || clip_bottom < 0)) {
+        set_error("acgpu_clip_batch: growing a frame in place would read bytes already overwritten; use src != dest");
+        return 0;
+    }
     {
-        HostStage hs(src, (size_t)width * height * Bpp, spitch, dest, (size_t)(new_w * new_h * Bpp), dpitch, nframes);
+        HostStage hs(src, inb, spitch, dest, outb, dpitch, nframes, stream, false, /*device_in_place=*/false);
         if (hs.staged)
             return hs.finish(hs.ok && acgpu_clip_batch(hs.dsrc, hs.ddst, width, height, Bpp, clip_left, clip_right, clip_top, clip_bottom,
                                                        black_pixel, hs.dsp, hs.ddp, nframes, hs.stream()));
     }
+    if (alias)      // cropping in place: every destination row lies at or before the source row it copies (tcvideo.c:229-246)
+        return through_temp(c, pick_stream(c, stream), dest, dpitch, outb, nframes, [&](uint8_t *t, size_t tp) {
+            return acgpu_clip_batch(src, t, width, height, Bpp, clip_left, clip_right, clip_top, clip_bottom, black_pixel, spitch, tp, nframes, stream) == 1; });
     TcvWindow p{};
     p.src = src; p.spitch = spitch; p.dst = dest; p.dpitch = dpitch;
     p.dBpl = (uint32_t)(new_w * Bpp); p.sBpl = (uint32_t)width * Bpp;
@@ -387,11 +477,20 @@ int acgpu_reduce_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     DevCtx *c = ctx();
     if (!c) return 0;
     if (nframes <= 0) return 1;
+    const size_t inb = (size_t)width * height * Bpp;
+    const size_t outb = (size_t)(reduce_w != 1 ? width / reduce_w : width) * (size_t)(height / reduce_h) * Bpp;
+    if (!norm_pitch("acgpu_reduce_batch", &spitch, inb, nframes) || !norm_pitch("acgpu_reduce_batch", &dpitch, outb, nframes)) return 0;
+    const int alias = alias_state("acgpu_reduce_batch", src, spitch, inb, dest, dpitch, outb, nframes);
+    if (alias < 0) return 0;
     {
-        const size_t outb = (size_t)(reduce_w != 1 ? width / reduce_w : width) * (size_t)(height / reduce_h) * Bpp;
-        HostStage hs(src, (size_t)width * height * Bpp, spitch, dest, outb, dpitch, nframes);
+        HostStage hs(src, inb, spitch, dest, outb, dpitch, nframes, stream, false, /*device_in_place=*/false);
         if (hs.staged)
             return hs.finish(hs.ok && acgpu_reduce_batch(hs.dsrc, hs.ddst, width, height, Bpp, reduce_w, reduce_h, hs.dsp, hs.ddp, nframes, hs.stream()));
+    }
+    if (alias) {    // in place: a kept pixel never moves to a higher address (tcvideo.c:694-715)
+        if (reduce_w == 1 && reduce_h == 1) return 1;
+        return through_temp(c, pick_stream(c, stream), dest, dpitch, outb, nframes, [&](uint8_t *t, size_t tp) {
+            return acgpu_reduce_batch(src, t, width, height, Bpp, reduce_w, reduce_h, spitch, tp, nframes, stream) == 1; });
     }
     cudaStream_t st = pick_stream(c, stream);
     if (reduce_w != 1)      // tcvideo.c:694-704
@@ -422,7 +521,10 @@ int acgpu_flip_v_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     if (nframes <= 0) return 1;
     {
         const size_t fb = (size_t)width * height * Bpp;
-        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (!norm_pitch("acgpu_flip_v_batch", &spitch, fb, nframes) || !norm_pitch("acgpu_flip_v_batch", &dpitch, fb, nframes)) return 0;
+        const int alias = alias_state("acgpu_flip_v_batch", src, spitch, fb, dest, dpitch, fb, nframes);
+        if (alias < 0 || (alias && nframes > 1 && spitch != dpitch)) { if (alias > 0) set_error("acgpu_flip_v_batch: in place needs one pitch"); return 0; }
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes, stream);
         if (hs.staged) return hs.finish(hs.ok && acgpu_flip_v_batch(hs.dsrc, hs.ddst, width, height, Bpp, hs.dsp, hs.ddp, nframes, hs.stream()));
     }
     cudaStream_t st = pick_stream(c, stream);
@@ -440,7 +542,10 @@ int acgpu_flip_h_batch(const uint8_t *src, uint8_t *dest, int width, int height,
     if (nframes <= 0) return 1;
     {
         const size_t fb = (size_t)width * height * Bpp;
-        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (!norm_pitch("acgpu_flip_h_batch", &spitch, fb, nframes) || !norm_pitch("acgpu_flip_h_batch", &dpitch, fb, nframes)) return 0;
+        const int alias = alias_state("acgpu_flip_h_batch", src, spitch, fb, dest, dpitch, fb, nframes);
+        if (alias < 0 || (alias && nframes > 1 && spitch != dpitch)) { if (alias > 0) set_error("acgpu_flip_h_batch: in place needs one pitch"); return 0; }
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes, stream);
         if (hs.staged) return hs.finish(hs.ok && acgpu_flip_h_batch(hs.dsrc, hs.ddst, width, height, Bpp, hs.dsp, hs.ddp, nframes, hs.stream()));
     }
     cudaStream_t st = pick_stream(c, stream);
@@ -459,7 +564,10 @@ int acgpu_gamma_correct_batch(const uint8_t *src, uint8_t *dest, int width, int 
     if (nframes <= 0) return 1;
     {
         const size_t fb = (size_t)width * height * Bpp;
-        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (!norm_pitch("acgpu_gamma_correct_batch", &spitch, fb, nframes) || !norm_pitch("acgpu_gamma_correct_batch", &dpitch, fb, nframes)) return 0;
+        const int alias = alias_state("acgpu_gamma_correct_batch", src, spitch, fb, dest, dpitch, fb, nframes);
+        if (alias < 0 || (alias && nframes > 1 && spitch != dpitch)) { if (alias > 0) set_error("acgpu_gamma_correct_batch: in place needs one pitch"); return 0; }
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes, stream);
         if (hs.staged) return hs.finish(hs.ok && acgpu_gamma_correct_batch(hs.dsrc, hs.ddst, width, height, Bpp, gamma, hs.dsp, hs.ddp, nframes, hs.stream()));
     }
     cudaStream_t st = pick_stream(c, stream);
@@ -486,7 +594,10 @@ int acgpu_antialias_batch(const uint8_t *src, uint8_t *dest, int width, int heig
     if (nframes <= 0) return 1;
     {
         const size_t fb = (size_t)width * height * Bpp;
-        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes);
+        if (!norm_pitch("acgpu_antialias_batch", &spitch, fb, nframes) || !norm_pitch("acgpu_antialias_batch", &dpitch, fb, nframes)) return 0;
+        const int alias = alias_state("acgpu_antialias_batch", src, spitch, fb, dest, dpitch, fb, nframes);
+        if (alias < 0 || (alias && nframes > 1 && spitch != dpitch)) { if (alias > 0) set_error("acgpu_antialias_batch: in place needs one pitch"); return 0; }
+        HostStage hs(src, fb, spitch, dest, fb, dpitch, nframes, stream);
         if (hs.staged) return hs.finish(hs.ok && acgpu_antialias_batch(hs.dsrc, hs.ddst, width, height, Bpp, weight, bias, hs.dsp, hs.ddp, nframes, hs.stream()));
     }
     cudaStream_t st = pick_stream(c, stream);
