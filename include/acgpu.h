@@ -222,8 +222,8 @@ typedef struct {
 int acgpu_chain_output(ImageFormat fmt, int width, int height, const acgpu_chain_op *ops, int nops,
                        ImageFormat *out_fmt, int *out_width, int *out_height);
 /* Device-resident: `nframes` frames a fixed pitch apart (0 = tightly packed), src is not modified, src and dest must not
- * overlap.  Intermediate frames live in the calling thread's temporary and the batch is walked in sub-batches small enough
- * for them to stay in L2 between stages.  Asynchronous on `stream`. */
+ * overlap.  Intermediate frames live in the calling thread's temporary (at most $ACGPU_CHAIN_SCRATCH_BYTES, default 2 GiB;
+ * longer batches are walked in sub-batches that fit).  Asynchronous on `stream`. */
 int acgpu_chain_batch(const uint8_t *src, ImageFormat fmt, int width, int height, size_t src_frame_pitch,
                       uint8_t *dest, size_t dest_frame_pitch, const acgpu_chain_op *ops, int nops, int nframes,
                       acgpu_stream_t stream);

@@ -166,7 +166,9 @@ def test_process_frame_chains(ac, tcv, conv, case):
 
 
 def test_chain_many_frames_crosses_pipeline_slots_and_sub_batches(ac, tcv, conv):
-    # 40 frames of 1080p: several chunks per pipeline slot on the host path, several L2 sub-batches on the device path
+    # 40 frames of 1080p: several chunks per pipeline slot on the host path; the device path is also run with a small
+    # temporary so the batch is cut into several sub-batches (the budget is read once per process: tests/knob_worker.py
+    # style subprocesses cover other values)
     w, h, nf = 1920, 1080, 40
     stages = [(CONVERT, F.IMG_RGB24), (FLIP_V,), (CONVERT, F.IMG_YUV422P)]
     uniq = frames_of(F.IMG_YUV420P, w, h, 4, 600)
@@ -272,3 +274,18 @@ def test_chain_rejections(ac):
     assert ac.lib.acgpu_chain_batch(buf.ptr, F.IMG_RGB24, w, h, 0, buf.ptr + 16, 0, ops, 1, 1, None) == 0
     assert ac.lib.acgpu_chain_batch(buf.ptr, F.IMG_RGB24, w, h, 0, buf.ptr, 0, ops, 1, 1, None) == 0
     buf.free()
+
+
+@pytest.mark.parametrize("budget", [1, 4_000_000, 9_000_000])
+def test_chain_batch_walks_sub_batches_when_the_temporary_is_small(budget):
+    """7 frames of 640x480 with room for 1, 2 and 4 frames per sub-batch (the last one partial)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    e = dict(os.environ)
+    e["ACGPU_CHAIN_SCRATCH_BYTES"] = str(budget)
+    e["PYTHONPATH"] = os.pathsep.join([root, here, e.get("PYTHONPATH", "")])
+    r = subprocess.run([sys.executable, os.path.join(here, "chain_worker.py")], capture_output=True, text=True, env=e, cwd=root, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().startswith("OK"), (r.stdout[-400:], r.stderr[-400:])

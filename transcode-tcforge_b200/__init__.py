@@ -19,6 +19,7 @@ from . import formats as F
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 LIB_PATH = os.environ.get("ACGPU_LIB") or os.path.join(_HERE, "libacgpu.so")   # ACGPU_LIB: A/B builds while profiling
+TCV_LIB_PATH = os.path.join(_HERE, "libtcvgpu.so")                              # libtcvideo's interface over libacgpu
 
 AC_NONE = 0
 AC_ALL = -1
@@ -132,6 +133,35 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "acgpu_chain_frames_host": (i32, [vp, i32, i32, i32, vp, C.POINTER(ChainOp), i32, i32]),
         "acgpu_chain_frames_host_multi": (i32, [vp, i32, i32, i32, vp, C.POINTER(ChainOp), i32, i32, i32]),
         "acgpu_shutdown": (None, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+#: every symbol include/tcvideo.h declares (libtcvideo/tcvideo.h:54-98)
+TCV_ABI_SYMBOLS = ["tcv_init", "tcv_free", "tcv_clip", "tcv_deinterlace", "tcv_resize", "tcv_zoom", "tcv_reduce", "tcv_flip_v",
+                   "tcv_flip_h", "tcv_gamma_correct", "tcv_antialias", "tcv_convert", "tcv_zoom_filter_to_string",
+                   "tcv_zoom_filter_from_string"]
+
+
+def load_tcv_library(path: str = TCV_LIB_PATH) -> C.CDLL:
+    """libtcvgpu.so with the reference's prototypes (handle first, then src, dest, width, height, Bpp, ...)."""
+    if not os.path.exists(path):
+        raise AcGpuError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    vp, i32, u8, dbl = C.c_void_p, C.c_int, C.c_uint8, C.c_double
+    plane = [vp, vp, vp, i32, i32, i32]
+    sig = {
+        "tcv_init": (vp, []), "tcv_free": (None, [vp]),
+        "tcv_clip": (i32, plane + [i32, i32, i32, i32, u8]), "tcv_deinterlace": (i32, plane + [i32]),
+        "tcv_resize": (i32, plane + [i32, i32, i32, i32]), "tcv_zoom": (i32, plane + [i32, i32, i32]),
+        "tcv_reduce": (i32, plane + [i32, i32]), "tcv_flip_v": (i32, plane), "tcv_flip_h": (i32, plane),
+        "tcv_gamma_correct": (i32, plane + [dbl]), "tcv_antialias": (i32, plane + [dbl, dbl]),
+        "tcv_convert": (i32, [vp, vp, vp, i32, i32, i32, i32]),
+        "tcv_zoom_filter_to_string": (C.c_char_p, [i32]), "tcv_zoom_filter_from_string": (i32, [C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -487,14 +487,17 @@ int acgpu_chain_batch(const uint8_t *src, ImageFormat fmt, int width, int height
         if (src < dest + dspan && dest < src + sspan) { set_error("acgpu_chain_batch: src and dest overlap"); return 0; }
     }
     cudaStream_t st = pick_stream(c, stream);
-    // Intermediate frames live in the thread's temporary.  The batch is walked in sub-batches small enough for the
-    // intermediates to stay in the 126 MB L2 between stages (they then cost no HBM traffic at all); a chain of one moving
-    // stage has no intermediate and runs as one launch over the whole batch.
+    // Intermediate frames live in the thread's temporary, two buffers of `sub` frames each; the batch is walked in
+    // sub-batches of that many frames.  Bigger is better: sub-batches small enough to keep the intermediates in the 126 MB
+    // L2 were measured and lost (UHD 420P -> RGB24 -> 422P: 48.9 k frames/s with one frame per launch, 64.9 k with two,
+    // 82.9 k with 32 or more -- launches of one or two frames leave most of the machine in the tail of each kernel, which
+    // costs more than the HBM round trip of the intermediate saves).  $ACGPU_CHAIN_SCRATCH_BYTES bounds the temporary
+    // (default 2 GiB); a chain of one moving stage has no intermediate and runs as one launch over the whole batch.
     const size_t tp = align_up(pl.max_bytes + 256, 256);
     const bool needs_scratch = !(pl.n_live == 0 || (pl.n_live == 1 && pl.n_out == 1 && !pl.two_pass));
     int sub = nframes;
     if (needs_scratch) {
-        static const size_t budget = [] { const char *e = getenv("ACGPU_CHAIN_L2_BYTES"); return e ? (size_t)atoll(e) : (size_t)48 << 20; }();
+        static const size_t budget = [] { const char *e = getenv("ACGPU_CHAIN_SCRATCH_BYTES"); return e ? (size_t)atoll(e) : (size_t)2 << 30; }();
         sub = (int)(budget / (2 * tp));
         if (sub < 1) sub = 1;
         if (sub > nframes) sub = nframes;
