@@ -7,7 +7,7 @@
 #   tcv_caller_legacy    reference header + reference libtcvideo over libacgpu  -- the unmodified per-row ac_* calls
 # `tests/c/<variant> time N` then times N frames of 1080p linear blend through each.
 set -e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 ROOT=$PWD
 PKG=$ROOT/transcode-tcforge_b200
 REF=${REF:-/root/reference}
