@@ -72,6 +72,17 @@ int   acgpu_memcpy_d2h(void *hptr, const void *dptr, size_t bytes, acgpu_stream_
 int   acgpu_memcpy_d2d(void *dptr, const void *sptr, size_t bytes, acgpu_stream_t stream);
 int   acgpu_memset(void *dptr, int value, size_t bytes, acgpu_stream_t stream);
 
+/* Frame-buffer plumbing.  transcode allocates every frame buffer with tc_bufalloc / tc_buffree (libtcutil/memutils.c:89-123:
+ * page-aligned malloc; libtc/tcframes.c:214-229 calls it for vframe_list_t.internal_video_buf_0 / _1).  acgpu_bufalloc /
+ * acgpu_buffree keep that contract on PAGE-LOCKED memory, so the unmodified per-frame ac_* / tcv_* calls on such frames DMA
+ * straight from and to them (INTEGRATION.md section 4 shows the two-line replacement).  A buffer that already exists is
+ * page-locked once with acgpu_host_register (whole pages; undo with acgpu_host_unregister before freeing it). */
+void *acgpu_bufalloc(size_t size);
+void  acgpu_buffree(void *ptr);
+int   acgpu_host_register(void *ptr, size_t size);
+int   acgpu_host_unregister(void *ptr);
+int   acgpu_pointer_kind(const void *ptr);        /* 0 pageable host, 1 page-locked host, 2 device */
+
 acgpu_stream_t acgpu_stream_create(void);
 void  acgpu_stream_destroy(acgpu_stream_t s);
 int   acgpu_stream_sync(acgpu_stream_t s);

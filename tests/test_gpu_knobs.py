@@ -21,6 +21,11 @@ ROOT = os.path.dirname(HERE)
     ({"ACGPU_TMA": "0"}, 3),               # tier 3: bulk (TMA) stores
     ({"ACGPU_TMA": "1"}, 3),               # tier 3: bulk-async staged loads
     ({"ACGPU_TMA": "2"}, 3),               # tier 3: staged loads + bulk stores
+    ({"ACGPU_TMA": "3"}, 3),               # tier 3: 2-D tensor-map stores (UTMASTG)
+    ({"ACGPU_TMA": "4"}, 3),               # tier 3: tensor-map loads (UTMALDG) and stores
+    ({"ACGPU_TMA": "5"}, 3),               # tier 3: tensor-map loads, LDS + STG stores
+    ({"ACGPU_TMA": "6"}, 3),               # tier 3: three-stage tensor-map loads, tensor-map stores
+    ({"ACGPU_TMA": "7"}, 3),               # tier 3: three-stage tensor-map loads, LDS + STG stores
 ], ids=lambda v: "-".join(f"{k[6:]}{x}" for k, x in v.items()) if isinstance(v, dict) else f"tier{v}")
 def test_knob_variants_match_the_checker(env, tier):
     e = dict(os.environ)

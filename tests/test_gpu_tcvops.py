@@ -108,6 +108,13 @@ def test_full_size_planes(ac, tcv, bpp):
             ("reduce", (1, 2), tcv.reduce(src, w, h, bpp, 1, 2)),
             ("reduce", (1, 1), tcv.reduce(src, w, h, bpp, 1, 1)),
             ("reduce", (4, 3), tcv.reduce(src, w, h, bpp, 4, 3)),
+            ("reduce", (3, 2), tcv.reduce(src, w, h, bpp, 3, 2)),
+            ("reduce", (3, 3), tcv.reduce(src, w, h, bpp, 3, 3)),
+            ("reduce", (4, 4), tcv.reduce(src, w, h, bpp, 4, 4)),
+            ("reduce", (5, 2), tcv.reduce(src, w, h, bpp, 5, 2)),
+            ("clip", (3, 5, 1, 1, 16), tcv.clip(src, w, h, bpp, 3, 5, 1, 1, black=16)),
+            ("clip", (1, 0, 0, 0, 16), tcv.clip(src, w, h, bpp, 1, 0, 0, 0, black=16)),
+            ("clip", (13, 2, 0, 3, 16), tcv.clip(src, w, h, bpp, 13, 2, 0, 3, black=16)),
             ("flip_v", (), tcv.flip_v(src, w, h, bpp)),
             ("flip_h", (), tcv.flip_h(src, w, h, bpp)),
             ("gamma_correct", (2.2,), tcv.gamma(src, w, h, bpp, 2.2)),
@@ -126,6 +133,86 @@ def test_full_size_planes(ac, tcv, bpp):
             ok_r, want = getattr(tcv, op)(src, w, h, bpp, inplace=True)
             ok, got = ac.plane_op_batch(op, f, want.size, w, h, bpp, inplace=True)
             assert ok == 1 and np.array_equal(got[0], want), op
+
+
+@pytest.mark.parametrize("bpp", [1, 3])
+def test_antialias_batches_cross_frames_inside_one_persistent_launch(ac, tcv, bpp):
+    """Five planes per launch (random, blocky, random, ...): the kernel's warps take 32-unit chunks of one frame in turn,
+    so chunk ranges end inside frames and the last chunk of a frame is partial (1080p: 129600 units = 4050 chunks;
+    720x576 at 4 pixels per unit is not a multiple of 32)."""
+    for (w, h) in [(1920, 1080), (724, 578), (64, 3)]:
+        imgs = [ck.splitmix_bytes(w * h * bpp, 11), tcv_cases.blocky_image(w, h, bpp, 12)]
+        frames = np.stack([imgs[i % 2] for i in range(5)])
+        want = [tcv.antialias(im, w, h, bpp, 0.333, 0.5)[1] for im in imgs]
+        ok, got = ac.plane_op_batch("antialias", frames, w * h * bpp, w, h, bpp, 0.333, 0.5, dst_gap=64, src_gap=16)
+        assert ok == 1, ac.last_error()
+        for i in range(5):
+            assert np.array_equal(got[i, : w * h * bpp], want[i % 2]), (w, h, bpp, i)
+        assert (got[:, w * h * bpp:] == 0x55).all()
+
+
+def test_in_place_rules(ac, tcv):
+    """src == dest (libtcvideo/tcvideo.c:180 allows it): accepted where the reference's sequential in-place result is the
+    out-of-place one -- and then equal to what the reference itself leaves in the buffer -- rejected elsewhere."""
+    w, h = 192, 64
+    for bpp in (1, 3):
+        src = ck.splitmix_bytes(w * h * bpp, 21)
+        f = src[None, :]
+
+        def both(op, ref_op, out_bytes, *args, ref_args=None):
+            ok, got = ac.plane_op_batch(op, f, out_bytes, w, h, bpp, *args, inplace=True)
+            assert ok == 1, (op, args, ac.last_error())
+            okr, want = ref_op(*(ref_args if ref_args is not None else args))
+            assert okr == 1 and np.array_equal(got[0, :out_bytes], want[:out_bytes]), (op, args, bpp)
+
+        ip = lambda name, *a: tcv._plane_op(name, src, 0, w, h, bpp, *a, inplace=True)
+        both("clip", lambda *a: ip("clip", *a), (w - 24) * (h - 6) * bpp, 8, 16, 2, 4, 7)
+        both("reduce", lambda *a: ip("reduce", *a), (w // 2) * (h // 2) * bpp, 2, 2)
+        both("reduce", lambda *a: ip("reduce", *a), (w // 3) * (h // 4) * bpp, 3, 4)
+        both("reduce", lambda *a: ip("reduce", *a), w * (h // 2) * bpp, 1, 2)
+        both("deinterlace", lambda *a: ip("deinterlace", *a), w * h * bpp, 0)            # interpolate
+        both("deinterlace", lambda *a: ip("deinterlace", *a), w * (h // 2) * bpp, 2)     # drop top field
+        both("deinterlace", lambda *a: ip("deinterlace", *a), w * (h // 2) * bpp, 3)     # drop bottom field
+        both("resize", lambda *a: ip("resize", *a), w * (h - 16) * bpp, 0, -2, 8, 8)
+        both("resize", lambda *a: ip("resize", *a), (w - 24) * h * bpp, -3, 0, 8, 8)
+        both("gamma_correct", lambda *a: ip("gamma", *a), w * h * bpp, 0.7)
+        # rejected: the reference's own in-place result depends on bytes it has already overwritten
+        for op, args in [("clip", (-8, 0, 0, 0, 0)), ("deinterlace", (1,)), ("resize", (0, 2, 8, 8)), ("resize", (3, 0, 8, 8)),
+                         ("antialias", (0.3, 0.5))]:
+            ok, _ = ac.plane_op_batch(op, f, w * h * bpp, w, h, bpp, *args, inplace=True)
+            assert ok == 0 and ac.last_error(), (op, args)
+    # partially overlapping device buffers are rejected outright
+    buf = ac.malloc(4 * w * h)
+    for fn, args in [(ac.lib.acgpu_flip_v_batch, ()), (ac.lib.acgpu_gamma_correct_batch, (1.5,)), (ac.lib.acgpu_reduce_batch, (2, 2))]:
+        assert fn(buf.ptr, buf.ptr + 64, w, h, 1, *args, 0, 0, 1, None) == 0 and "overlap" in ac.last_error()
+    buf.free()
+
+
+def test_staged_calls_order_after_the_callers_stream(ac, tcv):
+    """A batched call that hands a device-resident source to a HOST destination runs on the thread's private stream; it
+    must wait for what the caller's own stream still has in flight (here: the conversion that produces the source)."""
+    F = ck.F
+    w, h, nf = 1920, 1080, 24
+    chk = ck.best_checker()
+    yuv = ck.random_frame(F.IMG_YUV420P, w, h, seed=31)
+    _, rgb = chk.convert(yuv, F.IMG_YUV420P, F.IMG_RGB24, w, h, pad=0)
+    _, want = tcv.flip_v(rgb, w, h, 3)
+    sfb, dfb = yuv.size, rgb.size
+    ds = ac.malloc(nf * sfb)
+    for i in range(nf):
+        ds.upload(yuv, offset=i * sfb)
+    dd = ac.malloc(nf * dfb).fill(0)
+    host = np.zeros(nf * dfb, np.uint8)
+    stream = ac.lib.acgpu_stream_create()
+    for _ in range(3):
+        dd.fill(0)
+        ac._ok(ac.imgconvert_batch(ds.ptr, F.IMG_YUV420P, sfb, dd.ptr, F.IMG_RGB24, dfb, w, h, nf, stream))     # asynchronous on `stream`
+        ac._ok(ac.lib.acgpu_flip_v_batch(dd.ptr, host.ctypes.data, w, h, 3, dfb, dfb, nf, stream))                # device -> host, staged
+        got = host.reshape(nf, dfb)
+        for i in (0, nf // 2, nf - 1):
+            assert np.array_equal(got[i], want), i
+    ac.lib.acgpu_stream_destroy(stream)
+    ds.free(); dd.free()
 
 
 def test_flips_are_involutions_and_commute(ac):

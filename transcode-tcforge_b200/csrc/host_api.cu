@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -673,6 +674,48 @@ void *acgpu_host_alloc(size_t bytes)
     return p;
 }
 void acgpu_host_free(void *hptr) { if (hptr) cudaFreeHost(hptr); }
+
+// ---- frame-buffer plumbing -----------------------------------------------------------------------
+// transcode allocates every frame buffer through tc_bufalloc (libtcutil/memutils.c:89-112: page-aligned malloc;
+// libtc/tcframes.c:214-229 calls it twice per video frame, for vframe_list_t.internal_video_buf_0 / _1).  The same contract
+// on page-locked memory makes every legacy ac_* / tcv_* call on those buffers a direct DMA instead of a staged copy.
+void *acgpu_bufalloc(size_t size)
+{
+    void *p = nullptr;
+    if (device_usable(nullptr) && bind_device() && cudaHostAlloc(&p, size ? size : 1, cudaHostAllocPortable) == cudaSuccess) return p;
+    cudaGetLastError();
+    // no device (the library will refuse to convert anyway): still hand out what tc_bufalloc promises, a page-aligned buffer
+    const long page = sysconf(_SC_PAGESIZE);
+    if (posix_memalign(&p, page > 0 ? (size_t)page : 4096, size ? size : 1) != 0) return nullptr;
+    return p;
+}
+
+void acgpu_buffree(void *ptr)
+{
+    if (!ptr) return;
+    if (classify(ptr) == PK_PINNED) cudaFreeHost(ptr);
+    else free(ptr);
+}
+
+// An existing buffer (one tc_bufalloc already returned, a decoder's own frame): page-lock it ONCE, when it is created --
+// not per call, which costs more than the copy it saves.  Whole pages are locked (the range is widened to page bounds).
+int acgpu_host_register(void *ptr, size_t size)
+{
+    if (!ptr || !size) { set_error("acgpu_host_register: empty range"); return 0; }
+    if (!bind_device()) return 0;
+    const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE), a = (uintptr_t)ptr & ~(page - 1), e = ((uintptr_t)ptr + size + page - 1) & ~(page - 1);
+    return check(cudaHostRegister(reinterpret_cast<void *>(a), e - a, cudaHostRegisterPortable), "acgpu_host_register") ? 1 : 0;
+}
+
+int acgpu_host_unregister(void *ptr)
+{
+    if (!ptr) return 0;
+    const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
+    return check(cudaHostUnregister(reinterpret_cast<void *>((uintptr_t)ptr & ~(page - 1))), "acgpu_host_unregister") ? 1 : 0;
+}
+
+// 0 = pageable host memory, 1 = page-locked host memory, 2 = device memory: which path a legacy call on `ptr` takes.
+int acgpu_pointer_kind(const void *ptr) { return bind_device() ? (int)classify(ptr) : 0; }
 
 static int copy_async(void *d, const void *s, size_t n, cudaMemcpyKind k, acgpu_stream_t st, const char *who)
 {

@@ -18,6 +18,8 @@
 // convert_fast() returns false and the generic tier runs.
 #include "fast_common.cuh"
 
+#include <cuda.h>      // CUtensorMap types only: the encoder is reached through cudaGetDriverEntryPoint, libcuda is not linked
+
 #include <stdlib.h>
 
 namespace acgpu {
@@ -69,6 +71,10 @@ __device__ const ChromaTabs16 g_tabs16 = make_tabs16();
 #define ACGPU_LUT16 1
 #endif
 constexpr int kBiasRB = ACGPU_LUT16 ? 4096 : 0, kBiasG = ACGPU_LUT16 ? 8192 : 0;
+#ifndef ACGPU_REPL444
+#define ACGPU_REPL444 16
+#endif
+constexpr int kReplCopies = ACGPU_REPL444;        // private copies of the chroma tables for 4:4:4 sources (0: none)
 
 // ---------------------------------------------------------------------------------------------------
 // K1: YUV (7 layouts) -> RGB (6 layouts).  aclib/img_yuv_rgb.c:58-136.
@@ -210,6 +216,15 @@ __global__ void __launch_bounds__(256, FLAT ? 4 : 5) k_yuv2rgb(FastParams p)   /
 #else
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs)[i];
 #endif
+    // 4:4:4 looks two table words up per PIXEL with uncorrelated indices: on one copy of the tables 55 % of the shared
+    // wavefronts were bank-conflict replays and the L1/shared pipe ran at 95 % (profiles/r1c_ncu_secondary_kernels.md).
+    // That layout gets kReplCopies private copies, interleaved (entry e of copy c = word e * kReplCopies + c) so that a lane only
+    // shares banks with the lanes of its own copy.  32 copies (64 KB: two blocks per SM) were conflict-free but LOST to the
+    // occupancy they cost (0.835 -> 0.625 of peak); 16 copies keep five blocks per SM and halve the replays.
+    constexpr bool kRepl = SRC == S444 && !BULK && ACGPU_LUT16 && kReplCopies > 0;
+    uint32_t *const rep = reinterpret_cast<uint32_t *>(s_stage + (blockDim.x / 32) * 32 * BPP * (BULK ? 2 : 1));
+    if (kRepl)
+        for (int i = threadIdx.x; i < 512 * kReplCopies; i += blockDim.x) rep[i] = reinterpret_cast<const uint32_t *>(&g_tabs16)[i / kReplCopies];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *stage = s_stage + warp * (32 * BPP) * (BULK ? 2 : 1);
@@ -327,8 +342,16 @@ __global__ void __launch_bounds__(256, FLAT ? 4 : 5) k_yuv2rgb(FastParams p)   /
                     uint4 uu = make_uint4(0, 0, 0, 0), vv = uu;
                     if (valid) { uu = ldg128(S1 + (size_t)u * 16); vv = ldg128(S2 + (size_t)u * 16); }
 #pragma unroll
-                    for (int s = 0; s < 16; s++)
-                        chroma_terms<SRC>(s_tab, byte_of(word_of(uu, s >> 2), s & 3), byte_of(word_of(vv, s >> 2), s & 3), cr[s], cg[s], cb[s]);
+                    for (int s = 0; s < 16; s++) {
+                        if (kRepl) {        // packed table words, consumed as they are by convert_row
+                            const uint32_t *rt = rep + (lane & (kReplCopies - 1));
+                            cr[s] = (int)rt[byte_of(word_of(vv, s >> 2), s & 3) * kReplCopies];
+                            cb[s] = (int)rt[(256u + byte_of(word_of(uu, s >> 2), s & 3)) * kReplCopies];
+                            cg[s] = 0;
+                        } else {
+                            chroma_terms<SRC>(s_tab, byte_of(word_of(uu, s >> 2), s & 3), byte_of(word_of(vv, s >> 2), s & 3), cr[s], cg[s], cb[s]);
+                        }
+                    }
                 } else if (SRC == S422) {
                     uint2 uu = make_uint2(0, 0), vv = uu;
                     if (valid) { uu = ldg64(S1 + (size_t)u * 8); vv = ldg64(S2 + (size_t)u * 8); }
@@ -542,10 +565,14 @@ bool launch_yuv2rgb(const FastParams &p, int nframes, cudaStream_t st)
     const int lanes_row = ((p.upr + 31) / 32) * 32;
     q.flat420 = SRC == S420 && !BULK && p.upr >= 32 && p.upr * 10 < lanes_row * 8
              && (uint64_t)p.upr * p.nrp < 0x7FFFFFFFu && flat420_enabled();
-    LaunchShape s = SRC != S420 ? shape_linear(p.nunits, nframes, 8)
+    constexpr bool kRepl = SRC == S444 && !BULK && ACGPU_LUT16 && kReplCopies > 0;       // private table copies (see the kernel)
+    LaunchShape s = SRC != S420 ? shape_linear(p.nunits, nframes, kRepl ? 4 : 8)
                   : q.flat420   ? shape_linear((uint32_t)(p.upr * p.nrp), nframes, 8)
                                 : shape_420(p.upr, p.nrp, nframes, 8);
-    const size_t smem = (size_t)(s.block.x / 32) * 32 * BPP * sizeof(uint4) * (BULK ? 2 : 1);
+    const size_t smem = (size_t)(s.block.x / 32) * 32 * BPP * sizeof(uint4) * (BULK ? 2 : 1) + (kRepl ? 512 * kReplCopies * sizeof(uint32_t) : 0);
+    if (kRepl && !check(cudaFuncSetAttribute(k_yuv2rgb<SRC, SWAP, BPP, AFIRST, BULK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "k_yuv2rgb smem"))
+        return false;
     if (SRC == S420 && !BULK && q.flat420) k_yuv2rgb<SRC, SWAP, BPP, AFIRST, false, (SRC == S420 && !BULK)><<<s.grid, s.block, smem, st>>>(q);
     else k_yuv2rgb<SRC, SWAP, BPP, AFIRST, BULK, false><<<s.grid, s.block, smem, st>>>(q);
     note_launch();
@@ -672,6 +699,191 @@ bool launch_yuv420_rgb24_tma(const FastParams &p, int nframes, cudaStream_t st)
     note_launch();
     ACGPU_CHECK_LAUNCH("k_yuv420_rgb24_tma");
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Tier 3c (experiment, selectable: $ACGPU_TMA = 3 / 4): YUV420P -> RGB24/BGR24 with real tensor maps.
+//   stores ($ACGPU_TMA=3 and 4): the RGB24 batch is a 3-D tensor [frame][row][w*3/8 x uint64]; a warp's two output rows
+//     (2 x 1536 bytes) leave shared memory with ONE cp.async.bulk.tensor.3d store of a {192, 2, 1} box (SASS UTMASTG) --
+//     no LDS read-back, no per-lane STG, no store address arithmetic, partial warps clipped by the tensor bounds;
+//   loads ($ACGPU_TMA=4): Y is [frame][row][w/4 x uint32] (box {128, 2, 1}), U and V are [frame][row/2][w/8 x uint32]
+//     (box {64, 1, 1}); each warp runs a two-stage pipeline of three tensor loads (SASS UTMALDG) per row pair onto an
+//     mbarrier, as tier 3b does with four 1-D bulk copies.
+// Tensor maps are encoded on the host per launch (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint: the library
+// links no libcuda) and passed as __grid_constant__ parameters.
+__device__ __forceinline__ void tensor_store_3d(const CUtensorMap *map, const void *ssrc, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(ssrc)),
+                 "r"(x), "r"(y), "r"(z) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tensor_load_3d(void *sdst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(sdst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+template <bool SWAP, bool LOADS, bool TSTORE, int STAGES>
+__global__ void __launch_bounds__(256, 3) k_yuv420_rgb24_tma2d(FastParams p, const __grid_constant__ CUtensorMap mapY,
+                                                               const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapV,
+                                                               const __grid_constant__ CUtensorMap mapO)
+{
+    constexpr int BPP = 3;
+    __shared__ uint32_t s_tab[512];
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    // per warp (bytes): output tiles (two of 2 x 1536 for tensor stores, one 1536-byte transpose buffer otherwise),
+    // [STAGES input stages of 1024 (Y) + 256 (U) + 256 (V)], the mbarriers
+    constexpr int kOutTile = 3072, kOut = TSTORE ? 2 * kOutTile : 1536, kInStage = 1536, kPerWarp = kOut + (LOADS ? STAGES * kInStage : 0) + 128;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const uint32_t *>(&g_tabs16)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wbase = s_raw + (size_t)warp * kPerWarp;
+    uint8_t *out0 = wbase, *in0 = wbase + kOut;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + kPerWarp - 128);
+    const int frame = blockIdx.y;
+    const size_t soff = (size_t)frame * p.spitch, doff = (size_t)frame * p.dpitch;
+    const uint8_t *Y = p.s0 + soff, *U = p.s1 + soff, *V = p.s2 + soff;
+    const int unit = blockIdx.z * blockDim.x + threadIdx.x, wu0 = blockIdx.z * blockDim.x + warp * 32;
+    const bool valid = unit < p.upr;
+    const int nvalid = min(32, p.upr - wu0);
+    if (nvalid <= 0) return;
+    if (LOADS && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int rp, int st) {       // lane 0 only
+        uint8_t *b = in0 + st * kInStage;
+        mbar_expect_tx(&bars[st], kInStage);
+        tensor_load_3d(b, &mapY, wu0 * 4, 2 * rp, frame, &bars[st]);            // x in uint32 elements: 16 pixels = 4
+        tensor_load_3d(b + 1024, &mapU, wu0 * 2, rp, frame, &bars[st]);
+        tensor_load_3d(b + 1280, &mapV, wu0 * 2, rp, frame, &bars[st]);
+    };
+    const int step = (int)gridDim.x;
+    int rp = blockIdx.x;
+    if (LOADS && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++)
+            if (rp + s * step < p.nrp) issue(rp + s * step, s);
+    }
+    for (int it = 0; rp < p.nrp; rp += step, it++) {
+        uint32_t y0[4] = {0, 0, 0, 0}, y1[4] = {0, 0, 0, 0};
+        uint2 uu = make_uint2(0, 0), vv = make_uint2(0, 0);
+        if (LOADS) {
+            const int st = it % STAGES;
+            if (lane == 0 && rp + (STAGES - 1) * step < p.nrp) issue(rp + (STAGES - 1) * step, (it + STAGES - 1) % STAGES);
+            mbar_wait(&bars[st], (it / STAGES) & 1);
+            const uint8_t *b = in0 + st * kInStage;
+            const uint4 a = reinterpret_cast<const uint4 *>(b)[lane], c = reinterpret_cast<const uint4 *>(b + 512)[lane];
+            y0[0] = a.x; y0[1] = a.y; y0[2] = a.z; y0[3] = a.w;
+            y1[0] = c.x; y1[1] = c.y; y1[2] = c.z; y1[3] = c.w;
+            uu = reinterpret_cast<const uint2 *>(b + 1024)[lane];
+            vv = reinterpret_cast<const uint2 *>(b + 1280)[lane];
+            __syncwarp();        // every lane has read this stage before lane 0 may refill it (STAGES - 1 trips from now)
+        } else if (valid) {
+            const uint8_t *yp = Y + (size_t)(2 * rp) * p.w + unit * 16;
+            const uint4 a = ldg128(yp), c = ldg128(yp + p.w);
+            y0[0] = a.x; y0[1] = a.y; y0[2] = a.z; y0[3] = a.w;
+            y1[0] = c.x; y1[1] = c.y; y1[2] = c.z; y1[3] = c.w;
+            const size_t co = (size_t)rp * (p.w >> 1) + unit * 8;
+            uu = ldg64(U + co);
+            vv = ldg64(V + co);
+        }
+        int cr[8], cg[8], cb[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            chroma_terms<S420>(reinterpret_cast<const int2 *>(s_tab), byte_of(s < 4 ? uu.x : uu.y, s & 3),
+                               byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+        uint32_t ow[12];
+        if (TSTORE) {
+            uint8_t *tile = out0 + (it & 1) * kOutTile;
+            if (lane == 0) bulk_wait_read<1>();      // this tile's previous store has been read out of shared memory
+            __syncwarp();
+            convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
+#pragma unroll
+            for (int k = 0; k < 3; k++) reinterpret_cast<uint4 *>(tile + lane * 48)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+            convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
+#pragma unroll
+            for (int k = 0; k < 3; k++) reinterpret_cast<uint4 *>(tile + 1536 + lane * 48)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tensor_store_3d(&mapO, tile, wu0 * 6, 2 * rp, frame);     // x in uint64 elements: 16 pixels = 48 bytes = 6
+        } else {
+            uint8_t *row0 = p.d0 + doff + ((size_t)(2 * rp) * p.w + (size_t)wu0 * 16) * BPP;
+            convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
+            store_row_rgb<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, row0, nvalid);
+            convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
+            store_row_rgb<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+        }
+    }
+    if (TSTORE && lane == 0) bulk_wait_all<0>();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// [frames][rows][row_bytes / elem] tensor of `elem`-byte unsigned elements, box {box_x, box_y, 1}
+static bool make_map3(CUtensorMap *m, const void *base, int elem, uint64_t row_bytes, uint64_t rows, uint64_t frames, uint64_t pitch,
+                      uint32_t box_x, uint32_t box_y)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return false; }
+    const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    const cuuint64_t dims[3] = {row_bytes / (uint64_t)elem, rows, frames}, strides[2] = {row_bytes, frames > 1 ? pitch : row_bytes * rows};
+    const cuuint32_t box[3] = {box_x, box_y, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+    return true;
+}
+
+template <bool SWAP, bool LOADS, bool TSTORE, int STAGES>
+bool launch_yuv420_rgb24_tma2d(const FastParams &p, int nframes, cudaStream_t st)
+{
+    CUtensorMap mY, mU, mV, mO;
+    const uint64_t w = (uint64_t)p.w, h = (uint64_t)p.nrp * 2, nf = (uint64_t)nframes;
+    if (!make_map3(&mO, p.d0, 8, w * 3, h, nf, p.dpitch, 192, 2)) return false;
+    if (LOADS) {
+        if (!make_map3(&mY, p.s0, 4, w, h, nf, p.spitch, 128, 2) || !make_map3(&mU, p.s1, 4, w / 2, h / 2, nf, p.spitch, 64, 1)
+            || !make_map3(&mV, p.s2, 4, w / 2, h / 2, nf, p.spitch, 64, 1))
+            return false;
+    } else {
+        mY = mU = mV = mO;      // unused
+    }
+    const LaunchShape s = shape_420(p.upr, p.nrp, nframes, 8);
+    const size_t smem = (size_t)(s.block.x / 32) * ((TSTORE ? 2 * 3072 : 1536) + (LOADS ? STAGES * 1536 : 0) + 128) + 128;
+    auto kern = k_yuv420_rgb24_tma2d<SWAP, LOADS, TSTORE, STAGES>;
+    if (!check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return false;
+    kern<<<s.grid, s.block, smem, st>>>(p, mY, mU, mV, mO);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_yuv420_rgb24_tma2d");
+    return true;
+}
+
+template <bool SWAP>
+bool launch_tma2d_mode(int mode, const FastParams &p, int nframes, cudaStream_t st)
+{
+    switch (mode) {
+    case 3: return launch_yuv420_rgb24_tma2d<SWAP, false, true, 2>(p, nframes, st);     // LDG loads, tensor stores
+    case 4: return launch_yuv420_rgb24_tma2d<SWAP, true, true, 2>(p, nframes, st);      // tensor loads (2 stages), tensor stores
+    case 5: return launch_yuv420_rgb24_tma2d<SWAP, true, false, 2>(p, nframes, st);     // tensor loads, LDS + STG stores
+    case 6: return launch_yuv420_rgb24_tma2d<SWAP, true, true, 3>(p, nframes, st);      // tensor loads (3 stages), tensor stores
+    default: return launch_yuv420_rgb24_tma2d<SWAP, true, false, 3>(p, nframes, st);    // 7: tensor loads (3 stages), LDS + STG stores
+    }
 }
 
 template <int SRC>
@@ -818,8 +1030,13 @@ bool convert_tma(const ConvertArgs &a)
     FastParams p;
     if (!fast_domain(a, &p) || p.ragged420) return false;
     // $ACGPU_TMA: 0 = bulk stores only (default tier 3), 1 = bulk-async staged loads + LDS/STG stores,
-    //             2 = bulk-async staged loads + bulk stores.  Loads need an even number of units per warp (w % 32 == 0).
+    //             2 = bulk-async staged loads + bulk stores, 3 = 2-D tensor-map stores, 4 = tensor-map loads and stores,
+    //             5 = tensor-map loads + LDS/STG stores, 6 / 7 = as 4 / 5 with a three-stage load pipeline.
+    //             Loads need an even number of units per warp (w % 32 == 0).
     static const int mode = [] { const char *e = getenv("ACGPU_TMA"); return e ? atoi(e) : 0; }();
+    if (mode >= 3 && a.srcfmt == IMG_YUV420P && a.w % 32 == 0 && a.h % 2 == 0 && p.upr <= 256 * 65535) {
+        return a.dstfmt == IMG_BGR24 ? launch_tma2d_mode<true>(mode, p, a.nframes, a.stream) : launch_tma2d_mode<false>(mode, p, a.nframes, a.stream);
+    }
     if (mode > 0 && a.srcfmt == IMG_YUV420P && a.w % 32 == 0) {
         const bool swap = a.dstfmt == IMG_BGR24;
         if (mode == 1) return swap ? launch_yuv420_rgb24_tma<true, false>(p, a.nframes, a.stream) : launch_yuv420_rgb24_tma<false, false>(p, a.nframes, a.stream);

@@ -31,10 +31,18 @@ __device__ __forceinline__ uint4 ld16_any(const uint8_t *p)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     if ((a & 15) == 0) return COHERENT ? *reinterpret_cast<const uint4 *>(p) : ldg128(p);
+    // the two aligned 16-byte blocks that hold the bytes (one L1 wavefront each for a warp of consecutive chunks; five
+    // 32-bit loads per chunk cost five), then a shift by whole words and one by bytes
+    const uint4 *q = reinterpret_cast<const uint4 *>(a & ~(uintptr_t)15);
+    const uint4 lo = COHERENT ? q[0] : __ldg(q), hi = COHERENT ? q[1] : __ldg(q + 1);
     const uint32_t sh = (uint32_t)(a & 3) * 8;
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    const uint32_t w0 = ld32<COHERENT>(q), w1 = ld32<COHERENT>(q + 1), w2 = ld32<COHERENT>(q + 2), w3 = ld32<COHERENT>(q + 3);
-    const uint32_t w4 = sh ? ld32<COHERENT>(q + 4) : 0u;
+    uint32_t w0, w1, w2, w3, w4;
+    switch ((a >> 2) & 3) {
+    case 0:  w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
+    case 1:  w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
+    case 2:  w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
+    default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
+    }
     return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
 
@@ -184,28 +192,88 @@ __global__ void __launch_bounds__(kThreads) k_reduce_w2(const uint8_t *src0, siz
     }
 }
 
+// reduce_w == RW (3 or 4), output rows a multiple of 16 pixels, aligned planes: a thread turns 16*RW source pixels
+// (RW*BPP 128-bit loads) into 16 destination pixels (BPP 128-bit stores); which source byte lands where is known at
+// compile time, so the selection is a handful of byte permutes instead of one byte load per destination byte.
+template <int BPP, int RW>
+__global__ void __launch_bounds__(kThreads) k_reduce_wn(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                         uint32_t w, uint32_t ow, uint32_t oh, uint32_t rh)
+{
+    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
+    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
+    const uint32_t upr = ow / 16, n = upr * oh, stride = gridDim.x * blockDim.x;
+    constexpr int NS = 4 * RW * BPP, ND = 4 * BPP;          // source / destination words per thread
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t y = i / upr, u = i - y * upr;
+        const uint8_t *s = src + ((size_t)y * rh * w + (size_t)u * 16 * RW) * BPP;
+        uint8_t *d = dst + ((size_t)y * ow + (size_t)u * 16) * BPP;
+        uint32_t S[NS], O[ND];
+#pragma unroll
+        for (int k = 0; k < NS / 4; k++) {
+            const uint4 v = ldg128(s + 16 * k);
+            S[4 * k] = v.x; S[4 * k + 1] = v.y; S[4 * k + 2] = v.z; S[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < ND; k++) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int ob = 4 * k + j, px = ob / BPP, ch = ob % BPP, sb = px * RW * BPP + ch;    // destination byte -> source byte
+                word |= ((S[sb >> 2] >> (8 * (sb & 3))) & 0xFFu) << (8 * j);
+            }
+            O[k] = word;
+        }
+#pragma unroll
+        for (int k = 0; k < ND / 4; k++) stg128(d + 16 * k, make_uint4(O[4 * k], O[4 * k + 1], O[4 * k + 2], O[4 * k + 3]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // tcv_flip_v (tcvideo.c:739-766): row y <-> row height-1-y.  Every thread owns one 16-byte column slice of a row PAIR:
 // it reads both slices, then writes both, so src == dest (which the reference allows, :757-762) needs no temporary.
+// UNROLL slices per thread are read before any is written.  The loads are coherent (src may be dest) and streaming
+// (ld.global.cs): with plain loads the in-place flip ran at 0.69 of the copy rate, with streaming ones at 1.0 for every
+// UNROLL measured (1, 2, 4) -- lines that are about to be overwritten should not stay in L1.
+template <int UNROLL>
 __global__ void __launch_bounds__(kThreads) k_flip_v(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
                                                       uint32_t Bpl, uint32_t h, int vec)
 {
     const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
     uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
-    const uint32_t ncr = (Bpl + 15) / 16, n = ((h + 1) / 2) * ncr, stride = gridDim.x * blockDim.x;
+    const uint32_t ncr = (Bpl + 15) / 16, n = ((h + 1) / 2) * ncr;
+    if (vec) {
+        const uint32_t per_block = kThreads * UNROLL;
+        for (uint32_t base = blockIdx.x * per_block; base < n; base += gridDim.x * per_block) {
+            uint4 a[UNROLL], b[UNROLL];
+            size_t oa[UNROLL], ob[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                const uint32_t i = base + k * kThreads + threadIdx.x;
+                if (i < n) {
+                    const uint32_t y = i / ncr, xb = (i - y * ncr) * 16, m = h - 1 - y;
+                    oa[k] = (size_t)y * Bpl + xb;
+                    ob[k] = (size_t)m * Bpl + xb;
+                    a[k] = __ldcs(reinterpret_cast<const uint4 *>(src + oa[k]));      // coherent (src may be dest), streaming
+                    b[k] = __ldcs(reinterpret_cast<const uint4 *>(src + ob[k]));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                if (base + k * kThreads + threadIdx.x < n) {
+                    stg128(dst + oa[k], b[k]);
+                    stg128(dst + ob[k], a[k]);
+                }
+        }
+        return;
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t y = i / ncr, xb = (i - y * ncr) * 16, m = h - 1 - y;
         const size_t oa = (size_t)y * Bpl + xb, ob = (size_t)m * Bpl + xb;
-        if (vec) {
-            const uint4 a = *reinterpret_cast<const uint4 *>(src + oa), b = *reinterpret_cast<const uint4 *>(src + ob);
-            stg128(dst + oa, b);
-            stg128(dst + ob, a);
-        } else {
-            const uint32_t cnt = min(16u, Bpl - xb);
-            uint8_t a[16], b[16];
-            for (uint32_t k = 0; k < cnt; k++) { a[k] = src[oa + k]; b[k] = src[ob + k]; }
-            for (uint32_t k = 0; k < cnt; k++) { dst[oa + k] = b[k]; dst[ob + k] = a[k]; }
-        }
+        const uint32_t cnt = min(16u, Bpl - xb);
+        uint8_t a[16], b[16];
+        for (uint32_t k = 0; k < cnt; k++) { a[k] = src[oa + k]; b[k] = src[ob + k]; }
+        for (uint32_t k = 0; k < cnt; k++) { dst[oa + k] = b[k]; dst[ob + k] = a[k]; }
     }
 }
 
@@ -382,10 +450,10 @@ __global__ void __launch_bounds__(kThreads) k_antialias(const uint8_t *src0, siz
 // the (usually sparse) pixels that really are smoothed are gathered into a per-warp queue and take the 9-tap table path
 // on full warps.
 //   NG = 4: 16 pixels per thread, 128-bit accesses (width % 16 == 0, 16-byte aligned planes); NG = 1: 32-bit accesses.
-__device__ __forceinline__ uint32_t diff_bits(uint32_t a, uint32_t b)      // bit 7 of each byte: |a - b| >= 25
+__device__ __forceinline__ uint32_t diff_bits(uint32_t a, uint32_t b)      // bit 7 of each byte: |a - b| >= 25 (other bits: don't care)
 {
     const uint32_t d = __vabsdiffu4(a, b);
-    return (((d & 0x7F7F7F7Fu) + 0x67676767u) | d) & 0x80808080u;
+    return ((d & 0x7F7F7F7Fu) + 0x67676767u) | d;
 }
 
 // Per-byte "differs" bits of the thread's W words -> per-PIXEL bits, left on the first byte of every pixel.
@@ -406,20 +474,26 @@ __device__ __forceinline__ void pixel_diff(const uint32_t *a, const uint32_t *b,
     }
 }
 
-template <int BPP, int NG>
-__global__ void __launch_bounds__(kThreads) k_antialias_vec(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
-                                                             const uint32_t *tables, uint32_t w, uint32_t h)
+// The four weight tables live in shared memory as 32 private copies, interleaved so that lane l only ever touches bank l:
+// entry e of table t for lane l is word ((t*256 + e) << 5) + l.  Nine lookups per smoothed byte with uncorrelated indices
+// conflicted 2.5 ways on a single 4 KB copy (61 % of all shared wavefronts, profiles/r1c_ncu_secondary_kernels.md); this
+// layout is conflict-free by construction.  128 KB per block, so one persistent block per SM walks the whole batch.
+constexpr int kAaTableWords = 1024 * 32;
+
+template <int BPP, int NG, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_antialias_vec(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
+                                                              const uint32_t *tables, uint32_t w, uint32_t h, uint32_t nframes)
 {
     constexpr int W = BPP * NG, PX = 4 * NG;                // words / pixels per thread
-    __shared__ uint32_t s_t[1024];
-    __shared__ uint32_t s_queue[kThreads / 32][32 * PX];    // per warp: the pixels (y*w + x) that take the 9-tap path
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_t[i] = __ldg(tables + i);
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t *const s_t = s_dyn;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *const queue = s_dyn + kAaTableWords + warp * (32 * PX);     // per warp: byte offsets of the pixels that take the 9-tap path
+    for (int i = threadIdx.x; i < kAaTableWords; i += THREADS) s_t[i] = __ldg(tables + (i >> 5));
     __syncthreads();
-    const uint8_t *src = src0 + (size_t)blockIdx.y * spitch;
-    uint8_t *dst = dst0 + (size_t)blockIdx.y * dpitch;
-    const uint32_t upr = w / PX, wpr = upr * W, n = upr * h, stride = gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t *queue = s_queue[threadIdx.x >> 5];
+    const uint32_t *const my_t = s_t + lane;
+    const uint32_t upr = w / PX, wpr = upr * W, n = upr * h;
+    const uint32_t chunks_per_frame = (n + 31) / 32, chunks = chunks_per_frame * nframes;      // a chunk = 32 units of one frame
     const ptrdiff_t Bpl = (ptrdiff_t)w * BPP;
     constexpr int SHL = BPP == 1 ? 24 : 8, SHR = BPP == 1 ? 8 : 24;       // funnel shifts that move the row by BPP bytes
     auto load_words = [](const uint32_t *p, uint32_t *out) {
@@ -434,8 +508,10 @@ __global__ void __launch_bounds__(kThreads) k_antialias_vec(const uint8_t *src0,
             for (int k = 0; k < W; k++) out[k] = __ldg(p + k);
         }
     };
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {      // warp-uniform trip count
-        const uint32_t i = base + lane;
+    for (uint32_t c = blockIdx.x * (THREADS / 32) + warp; c < chunks; c += gridDim.x * (THREADS / 32)) {     // warp-uniform
+        const uint32_t frame = c / chunks_per_frame, i = (c - frame * chunks_per_frame) * 32 + lane;
+        const uint8_t *src = src0 + (size_t)frame * spitch;
+        uint8_t *dst = dst0 + (size_t)frame * dpitch;
         uint32_t S[W], any = 0, y = 0, u = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) S[k] = 0;
@@ -485,9 +561,34 @@ __global__ void __launch_bounds__(kThreads) k_antialias_vec(const uint8_t *src0,
                 for (int k = 0; k < W; k++) stg32(ow + 4 * k, C[k]);
             }
         }
-        // Smoothed pixels are usually sparse: gather the warp's into a dense queue so the 9-tap work runs on full
-        // warps, then overwrite those pixels (after the copies above; __syncwarp orders the two stores).
-        if (__any_sync(0xFFFFFFFFu, any != 0)) {
+        // The pixels that ARE smoothed overwrite their bytes after the copies above (each byte is written by the lane that
+        // smooths it; __syncwarp orders the two stores).  A warp with only a few of them lets the owning lanes do the 9-tap
+        // work themselves; a warp with many gathers them into a dense queue first so the work runs on full warps.
+        auto smooth_pixel = [&](uint32_t off) {
+            const uint8_t *cc = src + off, *uu = cc - Bpl, *dd = cc + Bpl;
+            uint8_t *o = dst + off;
+#pragma unroll
+            for (int k = 0; k < BPP; k++) {
+                const uint32_t sum = my_t[(768u + uu[k - BPP]) << 5] + my_t[(512u + uu[k]) << 5] + my_t[(768u + uu[k + BPP]) << 5]
+                                   + my_t[(256u + cc[k - BPP]) << 5] + my_t[(uint32_t)cc[k] << 5]   + my_t[(256u + cc[k + BPP]) << 5]
+                                   + my_t[(768u + dd[k - BPP]) << 5] + my_t[(512u + dd[k]) << 5] + my_t[(768u + dd[k + BPP]) << 5]
+                                   + 32768u;
+                o[k] = (uint8_t)(sum >> 16);
+            }
+        };
+        const uint32_t flagged = __ballot_sync(0xFFFFFFFFu, any != 0);
+        if (flagged) {
+            const uint32_t b0 = (y * wpr + u * W) * 4;            // byte offset of the thread's first word in the frame
+            if (__popc(flagged) <= 3) {
+                __syncwarp();
+                if (any) {
+#pragma unroll
+                    for (int k = 0; k < W; k++)
+                        for (uint32_t f = S[k]; f; f &= f - 1) smooth_pixel(b0 + (uint32_t)(4 * k + ((__ffs(f) - 1) >> 3)));
+                }
+                __syncwarp();
+                continue;
+            }
             uint32_t mine = 0;
 #pragma unroll
             for (int k = 0; k < W; k++) mine += __popc(S[k]);
@@ -500,25 +601,12 @@ __global__ void __launch_bounds__(kThreads) k_antialias_vec(const uint8_t *src0,
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
             if (mine) {
                 uint32_t slot = incl - mine;
-                const uint32_t px0 = y * w + u * PX;
 #pragma unroll
                 for (int k = 0; k < W; k++)
-                    for (uint32_t f = S[k]; f; f &= f - 1) queue[slot++] = px0 + (uint32_t)(4 * k + ((__ffs(f) - 1) >> 3)) / BPP;
+                    for (uint32_t f = S[k]; f; f &= f - 1) queue[slot++] = b0 + (uint32_t)(4 * k + ((__ffs(f) - 1) >> 3));
             }
             __syncwarp();
-            for (uint32_t r = lane; r < total; r += 32) {
-                const uint32_t px = queue[r];
-                const uint8_t *c = src + (size_t)px * BPP;
-#pragma unroll
-                for (int k = 0; k < BPP; k++) {
-                    const uint8_t *q = c + k;
-                    const uint32_t sum = s_t[768 + __ldg(q - Bpl - BPP)] + s_t[512 + __ldg(q - Bpl)] + s_t[768 + __ldg(q - Bpl + BPP)]
-                                       + s_t[256 + __ldg(q - BPP)] + s_t[__ldg(q)] + s_t[256 + __ldg(q + BPP)]
-                                       + s_t[768 + __ldg(q + Bpl - BPP)] + s_t[512 + __ldg(q + Bpl)] + s_t[768 + __ldg(q + Bpl + BPP)]
-                                       + 32768u;
-                    dst[(size_t)px * BPP + k] = (uint8_t)(sum >> 16);
-                }
-            }
+            for (uint32_t r = lane; r < total; r += 32) smooth_pixel(queue[r]);
             __syncwarp();
         }
     }
@@ -552,6 +640,16 @@ bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t d
         ACGPU_CHECK_LAUNCH("k_reduce_w2");
         return true;
     }
+    if ((rw == 3 || rw == 4) && ow % 16 == 0 && ((size_t)w * Bpp) % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes)) {
+        const dim3 gn = grid_for((uint64_t)(ow / 16) * oh, nframes);
+        if (Bpp == 1 && rw == 3) k_reduce_wn<1, 3><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
+        else if (Bpp == 1) k_reduce_wn<1, 4><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
+        else if (rw == 3) k_reduce_wn<3, 3><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
+        else k_reduce_wn<3, 4><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
+        note_launch();
+        ACGPU_CHECK_LAUNCH("k_reduce_wn");
+        return true;
+    }
     const dim3 g = grid_for((n + 3) / 4, nframes);
     const int vec = ((uintptr_t)dst & 3) == 0 && (nframes <= 1 || dpitch % 4 == 0);
     if (Bpp == 1) k_reduce<1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rw, rh, vec);
@@ -566,7 +664,7 @@ bool tcv_flip_v_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t d
     const uint32_t Bpl = (uint32_t)w * Bpp;
     const int vec = Bpl % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes);
     const uint64_t n = (uint64_t)((h + 1) / 2) * ((Bpl + 15) / 16);
-    k_flip_v<<<grid_for(n, nframes), kThreads, 0, st>>>(src, spitch, dst, dpitch, Bpl, h, vec);
+    k_flip_v<2><<<grid_for(n / 2 + 1, nframes), kThreads, 0, st>>>(src, spitch, dst, dpitch, Bpl, h, vec);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_flip_v");
     return true;
@@ -601,11 +699,25 @@ bool tcv_antialias_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_
                   && (nframes <= 1 || (spitch % 4 == 0 && dpitch % 4 == 0));
     if (vec) {
         const bool wide = w % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes);
-        const dim3 g = grid_for((uint64_t)(w / (wide ? 16 : 4)) * h, nframes, 8);
-        if (wide && Bpp == 1) k_antialias_vec<1, 4><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
-        else if (wide) k_antialias_vec<3, 4><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
-        else if (Bpp == 1) k_antialias_vec<1, 1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
-        else k_antialias_vec<3, 1><<<g, kThreads, 0, st>>>(src, spitch, dst, dpitch, d_tables, w, h);
+        // one persistent block per SM (its 128 KB of replicated tables fill most of the SM's shared memory); warps take
+        // chunks of 32 units of one frame in turn, so the blocks stay balanced whatever the number of frames is
+        const uint32_t units = (uint32_t)(w / (wide ? 16 : 4)) * (uint32_t)h, chunks_per_frame = (units + 31) / 32;
+        auto launch = [&](auto kern, int threads, int px) {
+            const size_t smem = ((size_t)kAaTableWords + (size_t)(threads / 32) * 32 * px) * sizeof(uint32_t);
+            // (per device and cheap: set on every launch rather than tracked per thread and device)
+            if (!check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "k_antialias_vec smem")) return false;
+            const uint64_t chunks = (uint64_t)chunks_per_frame * nframes;
+            const uint64_t want = (chunks + threads / 32 - 1) / (threads / 32);
+            const unsigned gx = (unsigned)(want < (uint64_t)sm_count() ? want : (uint64_t)sm_count());
+            kern<<<gx, threads, smem, st>>>(src, spitch, dst, dpitch, d_tables, (uint32_t)w, (uint32_t)h, (uint32_t)nframes);
+            return true;
+        };
+        bool ok;
+        if (wide && Bpp == 1) ok = launch(k_antialias_vec<1, 4, 1024>, 1024, 16);
+        else if (wide) ok = launch(k_antialias_vec<3, 4, 512>, 512, 16);
+        else if (Bpp == 1) ok = launch(k_antialias_vec<1, 1, 1024>, 1024, 4);
+        else ok = launch(k_antialias_vec<3, 1, 512>, 512, 4);
+        if (!ok) return false;
         note_launch();
         ACGPU_CHECK_LAUNCH("k_antialias_vec");
         return true;
