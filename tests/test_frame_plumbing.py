@@ -67,5 +67,6 @@ def test_frame_buffers_are_page_locked_and_calls_match_the_checker(size):
     assert got["flip_v"] == fnv(flipped)
     _, y422 = chk.convert(flipped, F.IMG_RGB24, F.IMG_YUV422P, w, h, pad=0)
     assert got["rgb24_yuv422p"] == fnv(y422)
-    _, bgr = chk.convert(yuv, F.IMG_YUV420P, F.IMG_BGR24, w, h, pad=0)
+    # by now buffer 0 holds the flipped RGB frame: its first w*h*3/2 bytes are what the last conversion reads as YUV420P
+    _, bgr = chk.convert(flipped[: F.frame_bytes(F.IMG_YUV420P, w, h)], F.IMG_YUV420P, F.IMG_BGR24, w, h, pad=0)
     assert got["yuv420p_bgr24"] == fnv(bgr)

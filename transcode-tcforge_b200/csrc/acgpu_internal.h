@@ -51,6 +51,9 @@ bool convert_generic(const ConvertArgs &a);
 bool convert_fast(const ConvertArgs &a);
 // Tier 3: the tier-2 YUV->RGB24 kernels with bulk (TMA) stores of the output tile (kernels_fast.cu); selectable only.
 bool convert_tma(const ConvertArgs &a);
+// The tier-3 variant that is chosen automatically where it beats tier 2 (YUV420P -> RGB, tensor-map staged loads); returns
+// false without launching when the call is outside its domain.
+bool convert_tma_auto(const ConvertArgs &a);
 
 // Fused RGB24 -> gray -> RGB24 in place (kernels_fast_rgb.cu); false when outside the vectorised domain.
 bool decolor_rgb24_fast(uint8_t *frames, size_t pitch, int w, int h, int nframes, cudaStream_t st);

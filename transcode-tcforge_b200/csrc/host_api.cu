@@ -159,22 +159,9 @@ bool arena_release(DevCtx *c, cudaStream_t st)
     return check(cudaEventRecord(c->arena_ev, st), "arena record");
 }
 
-namespace {
+int pointer_kind(const void *p) { return (int)classify(p); }
 
-bool ensure_bounce(DevCtx *c, size_t bytes)
-{
-    if (bytes <= c->bounce_cap) return true;
-    if (c->bounce) {
-        cudaStreamSynchronize(c->stream);
-        cudaFreeHost(c->bounce);
-        c->bounce = nullptr;
-        c->bounce_cap = 0;
-    }
-    const size_t cap = bytes + bytes / 4 + (1 << 20);
-    if (!check(cudaHostAlloc(&c->bounce, cap, cudaHostAllocDefault), "cudaHostAlloc(bounce)")) return false;
-    c->bounce_cap = cap;
-    return true;
-}
+namespace {
 
 // Waits for the thread's stream at the end of a legacy host-pointer call.  A few concurrent callers spin (lowest
 // latency); when more threads than that are inside staged calls at once -- 16 frame threads on a 16-core host -- they
@@ -195,6 +182,83 @@ bool wait_stream(DevCtx *c, int concurrent_callers, const char *who)
 // async DMA and do not serialise behind the driver's single pageable staging path (measured: 2.2 k frames/s flat).
 std::atomic<int> g_staged_calls{0};
 
+
+// ---- parallel host copies ---------------------------------------------------------------------------------------------
+// A lone caller on pageable frames is bound by its own memcpy into / out of pinned memory (~10 GB/s on one core; the link
+// moves 55).  A few helper threads share those copies.  Process-wide, created on first use, never joined (see g_workers).
+class CopyPool {
+    struct Job { uint8_t *d; const uint8_t *s; size_t n; std::atomic<int> *left; };
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<Job> q;
+    int nthreads = 0;
+
+    void worker()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [this] { return !q.empty(); });
+            Job j = q.back();
+            q.pop_back();
+            lk.unlock();
+            memcpy(j.d, j.s, j.n);
+            j.left->fetch_sub(1, std::memory_order_release);
+            lk.lock();
+        }
+    }
+
+public:
+    static CopyPool &get()
+    {
+        static CopyPool *pool = [] {
+            CopyPool *p = new CopyPool();      // leaked on purpose: its threads must not be joined at process exit
+            const char *e = getenv("ACGPU_COPY_THREADS");
+            int n = e ? atoi(e) : 3;
+            const int cores = (int)std::thread::hardware_concurrency();
+            if (n > cores - 1) n = cores - 1;
+            if (n < 0) n = 0;
+            p->nthreads = n;
+            for (int i = 0; i < n; i++) std::thread([p] { p->worker(); }).detach();
+            return p;
+        }();
+        return *pool;
+    }
+    // copies n bytes with the helpers' aid; the caller takes the last piece itself and returns when all are done
+    void copy(uint8_t *d, const uint8_t *s, size_t n, bool parallel)
+    {
+        constexpr size_t kPiece = 256u << 10;
+        if (!parallel || nthreads == 0 || n < 2 * kPiece) { memcpy(d, s, n); return; }
+        const int pieces = (int)std::min<size_t>((size_t)nthreads + 1, n / kPiece);
+        const size_t each = (n / (size_t)pieces + 63) & ~(size_t)63;
+        std::atomic<int> left{pieces - 1};
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (int i = 0; i + 1 < pieces; i++) q.push_back(Job{d + (size_t)i * each, s + (size_t)i * each, each, &left});
+        }
+        cv.notify_all();
+        const size_t done = (size_t)(pieces - 1) * each;
+        memcpy(d + done, s + done, n - done);
+        while (left.load(std::memory_order_acquire) > 0) {
+            // help with whatever is still queued (another caller's pieces count too) instead of spinning idle
+            Job j{};
+            bool have = false;
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (!q.empty()) { j = q.back(); q.pop_back(); have = true; }
+            }
+            if (have) { memcpy(j.d, j.s, j.n); j.left->fetch_sub(1, std::memory_order_release); }
+        }
+    }
+};
+
+bool ensure_ring(DevCtx *c)
+{
+    if (c->ring) return true;
+    if (!check(cudaHostAlloc(&c->ring, DevCtx::kRingSlots * DevCtx::kRingSlotBytes, cudaHostAllocDefault), "cudaHostAlloc(ring)")) return false;
+    for (cudaEvent_t &e : c->ring_ev)
+        if (!check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return false;
+    return true;
+}
 
 void plane_sizes(int fmt, int w, int h, size_t out[3], int *np)
 {
@@ -236,8 +300,9 @@ bool overwrites_whole_dest(int sfmt, int dfmt, int w, int h)
 
 bool run_convert(const ConvertArgs &a)
 {
-    // Automatic order: vectorised tier, else generic.  Tier 3 (bulk/TMA stores) is selectable but NOT the default:
-    // measured 2-3 % slower than tier 2 on the headline pair (profiles/r1_experiments.md).
+    // Automatic order: the tensor-map staged form of tier 3 where it is measured faster (YUV420P -> RGB on wide frames),
+    // the vectorised tier, else generic.  The other tier-3 variants (bulk / tensor stores) are selectable only: they
+    // measured slower than tier 2 (profiles/r1_experiments.md, profiles/r2_tma_tensor_maps.md).
     const int force = tls.force_tier;
     tls.err[0] = 0;      // a tier that declines a call leaves this empty; a failed launch leaves its CUDA error
     if (force == 3) {
@@ -245,6 +310,8 @@ bool run_convert(const ConvertArgs &a)
         if (!tls.err[0]) set_error("tier 3 (bulk stores) does not cover this pair/size/alignment");
         return false;
     }
+    if (force == 0 && convert_tma_auto(a)) { tls.last_tier = 3; return true; }
+    if (tls.err[0]) return false;
     if ((force == 0 || force == 2) && convert_fast(a)) { tls.last_tier = 2; return true; }
     if (tls.err[0]) return false;                       // a launch failed: do not paper over it with another tier
     if (force == 2) { set_error("tier 2 (vectorised) does not cover this pair/size/alignment"); return false; }
@@ -268,6 +335,75 @@ bool fold_yv12(uint8_t *const *src, int *sfmt, uint8_t *const *dst, int *dfmt, I
     if (*dfmt == IMG_YV12) { *dfmt = IMG_YUV420P; uint8_t *t = di->p[1]; di->p[1] = di->p[2]; di->p[2] = t; }
     return true;
 }
+
+}  // namespace
+
+StagedCall::StagedCall() : others(g_staged_calls.fetch_add(1)) {}
+StagedCall::~StagedCall() { g_staged_calls.fetch_sub(1); }
+
+bool staged_h2d(DevCtx *c, uint8_t *d, size_t dpitch, const uint8_t *h, size_t hpitch, size_t width, size_t rows, cudaStream_t st,
+                int host_kind, bool lone_caller)
+{
+    if (!width || !rows) return true;
+    if (host_kind != PK_HOST)       // page-locked: the copy engine reads the caller's memory directly
+        return check(cudaMemcpy2DAsync(d, dpitch, h, hpitch, width, rows, cudaMemcpyHostToDevice, st), "H2D");
+    if (!ensure_ring(c)) return false;
+    CopyPool &pool = CopyPool::get();
+    for (size_t r = 0; r < rows; r++)
+        for (size_t off = 0; off < width; off += DevCtx::kRingSlotBytes) {
+            const size_t n = std::min(DevCtx::kRingSlotBytes, width - off);
+            const int slot = c->ring_next;
+            c->ring_next = (slot + 1) % DevCtx::kRingSlots;
+            uint8_t *b = c->ring + (size_t)slot * DevCtx::kRingSlotBytes;
+            if (!check(cudaEventSynchronize(c->ring_ev[slot]), "ring wait")) return false;       // its previous DMA has drained
+            pool.copy(b, h + r * hpitch + off, n, lone_caller);
+            if (!check(cudaMemcpyAsync(d + r * dpitch + off, b, n, cudaMemcpyHostToDevice, st), "H2D")
+                || !check(cudaEventRecord(c->ring_ev[slot], st), "ring record"))
+                return false;
+        }
+    return true;
+}
+
+bool staged_d2h(DevCtx *c, uint8_t *h, size_t hpitch, const uint8_t *d, size_t dpitch, size_t width, size_t rows, cudaStream_t st,
+                int host_kind, bool lone_caller)
+{
+    if (!width || !rows) return true;
+    if (host_kind != PK_HOST)
+        return check(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, rows, cudaMemcpyDeviceToHost, st), "D2H");
+    if (!ensure_ring(c)) return false;
+    CopyPool &pool = CopyPool::get();
+    // chunk list in order; DMAs run kRingSlots - 1 chunks ahead of the host copies
+    struct Chunk { size_t r, off, n; int slot; };
+    const size_t per_row = (width + DevCtx::kRingSlotBytes - 1) / DevCtx::kRingSlotBytes, total = per_row * rows;
+    auto chunk_at = [&](size_t i) {
+        Chunk k;
+        k.r = i / per_row;
+        k.off = (i - k.r * per_row) * DevCtx::kRingSlotBytes;
+        k.n = std::min(DevCtx::kRingSlotBytes, width - k.off);
+        k.slot = (int)((c->ring_next + i) % DevCtx::kRingSlots);
+        return k;
+    };
+    auto issue = [&](size_t i) {
+        const Chunk k = chunk_at(i);
+        // the slot's previous use was a host copy that has completed (d2h) or an upload whose event is waited here
+        if (!check(cudaEventSynchronize(c->ring_ev[k.slot]), "ring wait")) return false;
+        return check(cudaMemcpyAsync(c->ring + (size_t)k.slot * DevCtx::kRingSlotBytes, d + k.r * dpitch + k.off, k.n, cudaMemcpyDeviceToHost, st), "D2H")
+            && check(cudaEventRecord(c->ring_ev[k.slot], st), "ring record");
+    };
+    const size_t ahead = DevCtx::kRingSlots - 1;
+    for (size_t i = 0; i < total && i < ahead; i++)
+        if (!issue(i)) return false;
+    for (size_t i = 0; i < total; i++) {
+        const Chunk k = chunk_at(i);
+        if (!check(cudaEventSynchronize(c->ring_ev[k.slot]), "D2H wait")) return false;
+        pool.copy(h + k.r * hpitch + k.off, c->ring + (size_t)k.slot * DevCtx::kRingSlotBytes, k.n, lone_caller);
+        if (i + ahead < total && !issue(i + ahead)) return false;
+    }
+    c->ring_next = (int)((c->ring_next + total) % DevCtx::kRingSlots);
+    return true;
+}
+
+namespace {
 
 // One frame through ac_imgconvert's legacy signature; planes may live on the host or on the device.
 bool convert_one(Image si, int sfmt, Image di, int dfmt, int w, int h)
@@ -304,52 +440,34 @@ bool convert_one(Image si, int sfmt, Image di, int dfmt, int w, int h)
     a.srcfmt = sfmt; a.dstfmt = dfmt; a.w = w; a.h = h; a.nframes = 1; a.stream = c->stream;
     a.src = si; a.dst = di;
     a.src.pitch = a.dst.pitch = 0;
-    // pageable caller memory: through the pinned bounce buffer when other threads are converting too
-    const bool src_pageable = sk == PK_HOST, dst_pageable = dk == PK_HOST;
+    // Pageable caller memory travels through the thread's ring of pinned slots (staged_h2d / staged_d2h): a lone caller --
+    // the usual transcode run has one frame thread -- gets its host copies spread over the helper threads; concurrent
+    // callers (src/frame_threads.c:174-228) each copy their own, pipelined with their DMAs.
     struct Busy {
         bool on;
         int  others;
         explicit Busy(bool o) : on(o), others(o ? g_staged_calls.fetch_add(1) : 0) {}
         ~Busy() { if (on) g_staged_calls.fetch_sub(1); }
     } busy(src_host || dst_host);
-    const bool bounce = (src_pageable || dst_pageable) && busy.others > 0 && ensure_bounce(c, need);
+    const bool lone = busy.others == 0;
     if (src_host)
         for (int p = 0; p < snp; p++) {
             a.src.p[p] = c->arena + soff[p];
-            const uint8_t *from = si.p[p];
-            if (bounce && src_pageable) {
-                memcpy(c->bounce + soff[p], si.p[p], ssz[p]);
-                from = c->bounce + soff[p];
-            }
-            if (!check(cudaMemcpyAsync(a.src.p[p], from, ssz[p], cudaMemcpyHostToDevice, c->stream), "H2D src plane"))
-                return false;
+            if (!staged_h2d(c, a.src.p[p], ssz[p], si.p[p], ssz[p], ssz[p], 1, c->stream, sk, lone)) return false;
         }
     if (dst_host) {
         const bool preload = !overwrites_whole_dest(sfmt, dfmt, w, h);
         for (int p = 0; p < dnp; p++) {
             a.dst.p[p] = c->arena + doff[p];
-            if (!preload) continue;
-            const uint8_t *from = di.p[p];
-            if (bounce && dst_pageable) {
-                memcpy(c->bounce + doff[p], di.p[p], dsz[p]);
-                from = c->bounce + doff[p];
-            }
-            if (!check(cudaMemcpyAsync(a.dst.p[p], from, dsz[p], cudaMemcpyHostToDevice, c->stream), "H2D dest plane"))
-                return false;
+            if (preload && !staged_h2d(c, a.dst.p[p], dsz[p], di.p[p], dsz[p], dsz[p], 1, c->stream, dk, lone)) return false;
         }
     }
     if (!run_convert(a)) return false;
     if (dst_host)
-        for (int p = 0; p < dnp; p++) {
-            uint8_t *to = (bounce && dst_pageable) ? c->bounce + doff[p] : di.p[p];
-            if (!check(cudaMemcpyAsync(to, a.dst.p[p], dsz[p], cudaMemcpyDeviceToHost, c->stream), "D2H dest plane"))
-                return false;
-        }
-    // callers that also memcpy through the bounce buffer do better spinning at every thread count measured
-    if (!wait_stream(c, bounce ? 0 : busy.others, "ac_imgconvert")) return false;
-    if (dst_host && bounce && dst_pageable)
-        for (int p = 0; p < dnp; p++) memcpy(di.p[p], c->bounce + doff[p], dsz[p]);
-    return true;
+        for (int p = 0; p < dnp; p++)
+            if (!staged_d2h(c, di.p[p], dsz[p], a.dst.p[p], dsz[p], dsz[p], 1, c->stream, dk, lone)) return false;
+    // callers that also copy through the ring do better spinning at every thread count measured
+    return wait_stream(c, (sk == PK_HOST || dk == PK_HOST) ? 0 : busy.others, "ac_imgconvert");
 }
 
 uint64_t fnv1a(const void *p, size_t n)
@@ -679,22 +797,37 @@ void acgpu_host_free(void *hptr) { if (hptr) cudaFreeHost(hptr); }
 // transcode allocates every frame buffer through tc_bufalloc (libtcutil/memutils.c:89-112: page-aligned malloc;
 // libtc/tcframes.c:214-229 calls it twice per video frame, for vframe_list_t.internal_video_buf_0 / _1).  The same contract
 // on page-locked memory makes every legacy ac_* / tcv_* call on those buffers a direct DMA instead of a staged copy.
+// Layout, as tc_bufalloc's own (memutils.c:93-106): [base ... | kind | base pointer | page-aligned user buffer].  Small
+// cudaHostAlloc blocks are sub-allocated at 256- or 512-byte granularity, so the page alignment is made here.
+static const uint64_t kBufPinned = 0x6163677075627566ull, kBufPlain = 0x6163677075626d61ull;
+
 void *acgpu_bufalloc(size_t size)
 {
-    void *p = nullptr;
-    if (device_usable(nullptr) && bind_device() && cudaHostAlloc(&p, size ? size : 1, cudaHostAllocPortable) == cudaSuccess) return p;
-    cudaGetLastError();
-    // no device (the library will refuse to convert anyway): still hand out what tc_bufalloc promises, a page-aligned buffer
-    const long page = sysconf(_SC_PAGESIZE);
-    if (posix_memalign(&p, page > 0 ? (size_t)page : 4096, size ? size : 1) != 0) return nullptr;
-    return p;
+    const long pg = sysconf(_SC_PAGESIZE);
+    const size_t page = pg > 0 ? (size_t)pg : 4096, total = (size ? size : 1) + page + 16;
+    void *base = nullptr;
+    uint64_t kind = kBufPinned;
+    if (!(device_usable(nullptr) && bind_device() && cudaHostAlloc(&base, total, cudaHostAllocPortable) == cudaSuccess)) {
+        cudaGetLastError();
+        // no device (the library will refuse to convert anyway): still hand out what tc_bufalloc promises, a page-aligned buffer
+        base = malloc(total);
+        kind = kBufPlain;
+        if (!base) return nullptr;
+    }
+    uint8_t *user = reinterpret_cast<uint8_t *>(align_up(reinterpret_cast<uintptr_t>(base) + 16, page));
+    reinterpret_cast<void **>(user)[-1] = base;
+    reinterpret_cast<uint64_t *>(user)[-2] = kind;
+    return user;
 }
 
 void acgpu_buffree(void *ptr)
 {
     if (!ptr) return;
-    if (classify(ptr) == PK_PINNED) cudaFreeHost(ptr);
-    else free(ptr);
+    void *base = reinterpret_cast<void **>(ptr)[-1];
+    const uint64_t kind = reinterpret_cast<uint64_t *>(ptr)[-2];
+    if (kind == kBufPinned) cudaFreeHost(base);
+    else if (kind == kBufPlain) free(base);
+    else fprintf(stderr, "libacgpu: acgpu_buffree(%p): not a buffer from acgpu_bufalloc\n", ptr);
 }
 
 // An existing buffer (one tc_bufalloc already returned, a decoder's own frame): page-lock it ONCE, when it is created --

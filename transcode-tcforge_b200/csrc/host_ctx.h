@@ -29,8 +29,12 @@ struct DevCtx {
     cudaEvent_t order_ev = nullptr;      // orders the private stream after a caller-named stream (see order_after)
     uint8_t *plane_stage = nullptr;      // device copies of HOST planes handed to the frame-granular entry points (its own
     size_t   plane_stage_cap = 0;        // buffer: those entry points may use the arena as their temporary meanwhile)
-    uint8_t *bounce = nullptr;           // pinned host mirror of the arena (pageable caller buffers go through it)
-    size_t   bounce_cap = 0;
+    // pageable caller memory travels through a ring of pinned slots: chunk k+1 is copied by the host while chunk k is DMA'd
+    static constexpr int kRingSlots = 4;
+    static constexpr size_t kRingSlotBytes = (size_t)1 << 20;
+    uint8_t *ring = nullptr;
+    cudaEvent_t ring_ev[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};   // slot's last DMA (either direction) is done
+    int      ring_next = 0;
     std::vector<Blob> blobs;
     cudaStream_t pipe_stream[kPipeSlots] = {nullptr, nullptr, nullptr};
     uint8_t *pipe_buf[kPipeSlots] = {nullptr, nullptr, nullptr};
@@ -55,7 +59,7 @@ struct ThreadCtx {
         if (process_exiting()) return;
         for (int d = 0; d < kMaxDev; d++) {
             DevCtx &c = dev[d];
-            if (!c.stream && !c.arena && !c.plane_stage && !c.bounce && c.blobs.empty() && !c.pipe_stream[0]) continue;
+            if (!c.stream && !c.arena && !c.plane_stage && !c.ring && c.blobs.empty() && !c.pipe_stream[0]) continue;
             if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
             cudaDeviceSynchronize();     // batched calls may have run on caller-supplied streams that still read our tables
             for (int s = 0; s < kPipeSlots; s++) {
@@ -65,7 +69,8 @@ struct ThreadCtx {
             for (Blob &b : c.blobs) cudaFree(b.dptr);
             if (c.arena) cudaFree(c.arena);
             if (c.plane_stage) cudaFree(c.plane_stage);
-            if (c.bounce) cudaFreeHost(c.bounce);
+            if (c.ring) cudaFreeHost(c.ring);
+            for (cudaEvent_t e : c.ring_ev) if (e) cudaEventDestroy(e);
             if (c.sleep_ev) cudaEventDestroy(c.sleep_ev);
             if (c.arena_ev) cudaEventDestroy(c.arena_ev);
             if (c.order_ev) cudaEventDestroy(c.order_ev);
@@ -81,6 +86,22 @@ DevCtx      *ctx();                                            // binds the thre
 cudaStream_t pick_stream(DevCtx *c, acgpu_stream_t s);         // the caller's stream, or the thread's own
 bool  order_after(DevCtx *c, acgpu_stream_t caller);           // private stream waits for what the caller's stream holds so far
 bool  is_device_pointer(const void *p);                        // device / managed memory (else pageable or page-locked host)
+int   pointer_kind(const void *p);                             // 0 pageable host, 1 page-locked host, 2 device
+// Host <-> device transfers of the staged (host-pointer) calls on stream `st`.  Page-locked memory is DMA'd directly and
+// asynchronously.  Pageable memory goes through the thread's ring of pinned slots in 1 MB chunks -- the host copy of one
+// chunk overlaps the DMA of the previous one -- and, when the caller is the only thread inside a staged call, the host
+// copies are spread over a small pool of helper threads (one core copies ~10 GB/s, PCIe moves 55).  `rows` chunks of
+// `width` bytes, `hpitch` / `dpitch` apart.  d2h with a pageable destination returns after the data has landed.
+bool  staged_h2d(DevCtx *c, uint8_t *d, size_t dpitch, const uint8_t *h, size_t hpitch, size_t width, size_t rows, cudaStream_t st,
+                 int host_kind, bool lone_caller);
+bool  staged_d2h(DevCtx *c, uint8_t *h, size_t hpitch, const uint8_t *d, size_t dpitch, size_t width, size_t rows, cudaStream_t st,
+                 int host_kind, bool lone_caller);
+// callers inside staged calls right now (this one included after enter): RAII
+struct StagedCall {
+    int others;
+    StagedCall();
+    ~StagedCall();
+};
 bool  ensure_arena(DevCtx *c, size_t bytes);
 bool  arena_acquire(DevCtx *c, cudaStream_t st);               // orders uses of the arena on different streams
 bool  arena_release(DevCtx *c, cudaStream_t st);

@@ -40,7 +40,9 @@ void build_resize_table(int oldsize, int newsize, std::vector<int32_t> &src, std
 // round trip per FRAME instead of one per ROW (tcv_deinterlace / tcv_resize call ac_average / ac_rescale per row).
 struct HostStage {
     DevCtx *c = nullptr;
-    bool staged = false, ok = true, dst_host = false;
+    bool staged = false, ok = true, dst_host = false, lone = true;
+    int dst_kind = 0;
+    StagedCall *busy = nullptr;
     const uint8_t *dsrc = nullptr;
     uint8_t *ddst = nullptr, *dest = nullptr;
     size_t dsp = 0, ddp = 0, dp_host = 0, out_bytes = 0;
@@ -54,10 +56,14 @@ struct HostStage {
               acgpu_stream_t caller_stream, bool preload_dest = false, bool device_in_place = true)
     {
         if (nframes <= 0 || tls.device_only > 0) return;
-        const bool src_host = !is_device_pointer(src);
-        dst_host = src == dst ? src_host : !is_device_pointer(dst);
+        const int src_kind = pointer_kind(src);
+        dst_kind = src == dst ? src_kind : pointer_kind(dst);
+        const bool src_host = src_kind != 2;
+        dst_host = dst_kind != 2;
         if (!src_host && !dst_host) return;
         staged = true;
+        busy = new StagedCall();
+        lone = busy->others == 0;
         c = ctx();
         if (!c) { ok = false; return; }
         // the staged sequence runs on the thread's private stream: a device-resident side may still be in flight on the
@@ -79,24 +85,26 @@ struct HostStage {
         }
         uint8_t *as = c->plane_stage, *ad = c->plane_stage + src_region;
         if (src_host) {
-            ok = check(cudaMemcpy2DAsync(as, dsp, src, sp_host, in_bytes, (size_t)nframes, cudaMemcpyHostToDevice, c->stream), "H2D planes");
+            ok = staged_h2d(c, as, dsp, src, sp_host, in_bytes, (size_t)nframes, c->stream, src_kind, lone);
             dsrc = as;
         } else {
             dsrc = src;
         }
         ddst = in_place ? const_cast<uint8_t *>(dsrc) : dst_host ? ad : dst;
         if (ok && preload_dest && dst_host && !in_place && outb)
-            ok = check(cudaMemcpy2DAsync(ad, ddp, dst, dp_host, outb, (size_t)nframes, cudaMemcpyHostToDevice, c->stream), "H2D dest planes");
+            ok = staged_h2d(c, ad, ddp, dst, dp_host, outb, (size_t)nframes, c->stream, dst_kind, lone);
     }
     acgpu_stream_t stream() const { return reinterpret_cast<acgpu_stream_t>(c->stream); }
     int finish(int launched)
     {
         bool good = ok && launched;
-        if (good && dst_host && out_bytes)
-            good = check(cudaMemcpy2DAsync(dest, dp_host, ddst, ddp, out_bytes, (size_t)nf, cudaMemcpyDeviceToHost, c->stream), "D2H planes");
+        if (good && dst_host && out_bytes) good = staged_d2h(c, dest, dp_host, ddst, ddp, out_bytes, (size_t)nf, c->stream, dst_kind, lone);
         if (c) good = check(cudaStreamSynchronize(c->stream), "frame operation") && good;
         return good ? 1 : 0;
     }
+    ~HostStage() { delete busy; }
+    HostStage(const HostStage &) = delete;
+    HostStage &operator=(const HostStage &) = delete;
 };
 
 // One pitch rule for every entry point: 0 means tightly packed frames, and consecutive frames must not overlap.

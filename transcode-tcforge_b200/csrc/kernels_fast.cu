@@ -72,9 +72,10 @@ __device__ const ChromaTabs16 g_tabs16 = make_tabs16();
 #endif
 constexpr int kBiasRB = ACGPU_LUT16 ? 4096 : 0, kBiasG = ACGPU_LUT16 ? 8192 : 0;
 #ifndef ACGPU_REPL444
-#define ACGPU_REPL444 16
+#define ACGPU_REPL444 0
 #endif
-constexpr int kReplCopies = ACGPU_REPL444;        // private copies of the chroma tables for 4:4:4 sources (0: none)
+constexpr int kReplCopies = ACGPU_REPL444 > 0 ? ACGPU_REPL444 : 1;     // private copies of the chroma tables for 4:4:4 sources
+constexpr bool kReplOn = ACGPU_REPL444 > 0;
 
 // ---------------------------------------------------------------------------------------------------
 // K1: YUV (7 layouts) -> RGB (6 layouts).  aclib/img_yuv_rgb.c:58-136.
@@ -219,9 +220,11 @@ __global__ void __launch_bounds__(256, FLAT ? 4 : 5) k_yuv2rgb(FastParams p)   /
     // 4:4:4 looks two table words up per PIXEL with uncorrelated indices: on one copy of the tables 55 % of the shared
     // wavefronts were bank-conflict replays and the L1/shared pipe ran at 95 % (profiles/r1c_ncu_secondary_kernels.md).
     // That layout gets kReplCopies private copies, interleaved (entry e of copy c = word e * kReplCopies + c) so that a lane only
-    // shares banks with the lanes of its own copy.  32 copies (64 KB: two blocks per SM) were conflict-free but LOST to the
-    // occupancy they cost (0.835 -> 0.625 of peak); 16 copies keep five blocks per SM and halve the replays.
-    constexpr bool kRepl = SRC == S444 && !BULK && ACGPU_LUT16 && kReplCopies > 0;
+    // shares banks with the lanes of its own copy.  MEASURED AND REJECTED (ACGPU_REPL444 = 0 is the default build): 32 copies
+    // (64 KB: two blocks per SM) are conflict-free but lose to the occupancy they cost, 0.835 -> 0.625 of peak; 16 copies
+    // keep five blocks per SM and reach 0.82 on random bytes but also on a smooth picture, where the single copy runs at
+    // 0.98 (neighbouring lanes hit the same words and the hardware broadcasts) -- profiles/r2_experiments.md.
+    constexpr bool kRepl = SRC == S444 && !BULK && ACGPU_LUT16 && kReplOn;
     uint32_t *const rep = reinterpret_cast<uint32_t *>(s_stage + (blockDim.x / 32) * 32 * BPP * (BULK ? 2 : 1));
     if (kRepl)
         for (int i = threadIdx.x; i < 512 * kReplCopies; i += blockDim.x) rep[i] = reinterpret_cast<const uint32_t *>(&g_tabs16)[i / kReplCopies];
@@ -565,7 +568,7 @@ bool launch_yuv2rgb(const FastParams &p, int nframes, cudaStream_t st)
     const int lanes_row = ((p.upr + 31) / 32) * 32;
     q.flat420 = SRC == S420 && !BULK && p.upr >= 32 && p.upr * 10 < lanes_row * 8
              && (uint64_t)p.upr * p.nrp < 0x7FFFFFFFu && flat420_enabled();
-    constexpr bool kRepl = SRC == S444 && !BULK && ACGPU_LUT16 && kReplCopies > 0;       // private table copies (see the kernel)
+    constexpr bool kRepl = SRC == S444 && !BULK && ACGPU_LUT16 && kReplOn;       // private table copies (see the kernel)
     LaunchShape s = SRC != S420 ? shape_linear(p.nunits, nframes, kRepl ? 4 : 8)
                   : q.flat420   ? shape_linear((uint32_t)(p.upr * p.nrp), nframes, 8)
                                 : shape_420(p.upr, p.nrp, nframes, 8);
@@ -723,17 +726,17 @@ __device__ __forceinline__ void tensor_load_3d(void *sdst, const CUtensorMap *ma
                      smem_u32(sdst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-template <bool SWAP, bool LOADS, bool TSTORE, int STAGES>
+template <bool SWAP, int BPP, bool AFIRST, bool LOADS, bool TSTORE, int STAGES>
 __global__ void __launch_bounds__(256, 3) k_yuv420_rgb24_tma2d(FastParams p, const __grid_constant__ CUtensorMap mapY,
                                                                const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapV,
                                                                const __grid_constant__ CUtensorMap mapO)
 {
-    constexpr int BPP = 3;
+    static_assert(!TSTORE || BPP == 3, "tensor stores cannot merge the untouched alpha byte");
     __shared__ uint32_t s_tab[512];
     extern __shared__ __align__(128) uint8_t s_raw[];
     // per warp (bytes): output tiles (two of 2 x 1536 for tensor stores, one 1536-byte transpose buffer otherwise),
     // [STAGES input stages of 1024 (Y) + 256 (U) + 256 (V)], the mbarriers
-    constexpr int kOutTile = 3072, kOut = TSTORE ? 2 * kOutTile : 1536, kInStage = 1536, kPerWarp = kOut + (LOADS ? STAGES * kInStage : 0) + 128;
+    constexpr int kOutTile = 3072, kOut = TSTORE ? 2 * kOutTile : 512 * BPP, kInStage = 1536, kPerWarp = kOut + (LOADS ? STAGES * kInStage : 0) + 128;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const uint32_t *>(&g_tabs16)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -795,7 +798,7 @@ __global__ void __launch_bounds__(256, 3) k_yuv420_rgb24_tma2d(FastParams p, con
         for (int s = 0; s < 8; s++)
             chroma_terms<S420>(reinterpret_cast<const int2 *>(s_tab), byte_of(s < 4 ? uu.x : uu.y, s & 3),
                                byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
-        uint32_t ow[12];
+        uint32_t ow[BPP * 4];
         if (TSTORE) {
             uint8_t *tile = out0 + (it & 1) * kOutTile;
             if (lane == 0) bulk_wait_read<1>();      // this tile's previous store has been read out of shared memory
@@ -811,10 +814,12 @@ __global__ void __launch_bounds__(256, 3) k_yuv420_rgb24_tma2d(FastParams p, con
             if (lane == 0) tensor_store_3d(&mapO, tile, wu0 * 6, 2 * rp, frame);     // x in uint64 elements: 16 pixels = 48 bytes = 6
         } else {
             uint8_t *row0 = p.d0 + doff + ((size_t)(2 * rp) * p.w + (size_t)wu0 * 16) * BPP;
-            convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
-            store_row_rgb<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, row0, nvalid);
-            convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
-            store_row_rgb<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, row0 + (size_t)p.w * BPP, nvalid);
+            prefetch_dest_row<BPP>(row0, lane, nvalid);
+            prefetch_dest_row<BPP>(row0 + (size_t)p.w * BPP, lane, nvalid);
+            convert_row<S420, SWAP, BPP, AFIRST>(y0, cr, cg, cb, ow);
+            store_row_rgb<BPP, AFIRST>(reinterpret_cast<uint4 *>(out0), lane, ow, row0, nvalid);
+            convert_row<S420, SWAP, BPP, AFIRST>(y1, cr, cg, cb, ow);
+            store_row_rgb<BPP, AFIRST>(reinterpret_cast<uint4 *>(out0), lane, ow, row0 + (size_t)p.w * BPP, nvalid);
         }
     }
     if (TSTORE && lane == 0) bulk_wait_all<0>();
@@ -851,22 +856,25 @@ static bool make_map3(CUtensorMap *m, const void *base, int elem, uint64_t row_b
     return true;
 }
 
-template <bool SWAP, bool LOADS, bool TSTORE, int STAGES>
+template <bool SWAP, int BPP, bool AFIRST, bool LOADS, bool TSTORE, int STAGES>
 bool launch_yuv420_rgb24_tma2d(const FastParams &p, int nframes, cudaStream_t st)
 {
     CUtensorMap mY, mU, mV, mO;
     const uint64_t w = (uint64_t)p.w, h = (uint64_t)p.nrp * 2, nf = (uint64_t)nframes;
-    if (!make_map3(&mO, p.d0, 8, w * 3, h, nf, p.dpitch, 192, 2)) return false;
     if (LOADS) {
         if (!make_map3(&mY, p.s0, 4, w, h, nf, p.spitch, 128, 2) || !make_map3(&mU, p.s1, 4, w / 2, h / 2, nf, p.spitch, 64, 1)
             || !make_map3(&mV, p.s2, 4, w / 2, h / 2, nf, p.spitch, 64, 1))
             return false;
-    } else {
-        mY = mU = mV = mO;      // unused
     }
+    if (TSTORE) {
+        if (!make_map3(&mO, p.d0, 8, w * 3, h, nf, p.dpitch, 192, 2)) return false;
+    } else {
+        mO = mY;                // unused
+    }
+    if (!LOADS) mY = mU = mV = mO;
     const LaunchShape s = shape_420(p.upr, p.nrp, nframes, 8);
-    const size_t smem = (size_t)(s.block.x / 32) * ((TSTORE ? 2 * 3072 : 1536) + (LOADS ? STAGES * 1536 : 0) + 128) + 128;
-    auto kern = k_yuv420_rgb24_tma2d<SWAP, LOADS, TSTORE, STAGES>;
+    const size_t smem = (size_t)(s.block.x / 32) * ((TSTORE ? 2 * 3072 : 512 * BPP) + (LOADS ? STAGES * 1536 : 0) + 128) + 128;
+    auto kern = k_yuv420_rgb24_tma2d<SWAP, BPP, AFIRST, LOADS, TSTORE, STAGES>;
     if (!check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return false;
     kern<<<s.grid, s.block, smem, st>>>(p, mY, mU, mV, mO);
     note_launch();
@@ -878,11 +886,22 @@ template <bool SWAP>
 bool launch_tma2d_mode(int mode, const FastParams &p, int nframes, cudaStream_t st)
 {
     switch (mode) {
-    case 3: return launch_yuv420_rgb24_tma2d<SWAP, false, true, 2>(p, nframes, st);     // LDG loads, tensor stores
-    case 4: return launch_yuv420_rgb24_tma2d<SWAP, true, true, 2>(p, nframes, st);      // tensor loads (2 stages), tensor stores
-    case 5: return launch_yuv420_rgb24_tma2d<SWAP, true, false, 2>(p, nframes, st);     // tensor loads, LDS + STG stores
-    case 6: return launch_yuv420_rgb24_tma2d<SWAP, true, true, 3>(p, nframes, st);      // tensor loads (3 stages), tensor stores
-    default: return launch_yuv420_rgb24_tma2d<SWAP, true, false, 3>(p, nframes, st);    // 7: tensor loads (3 stages), LDS + STG stores
+    case 3: return launch_yuv420_rgb24_tma2d<SWAP, 3, false, false, true, 2>(p, nframes, st);     // LDG loads, tensor stores
+    case 4: return launch_yuv420_rgb24_tma2d<SWAP, 3, false, true, true, 2>(p, nframes, st);      // tensor loads (2 stages), tensor stores
+    case 5: return launch_yuv420_rgb24_tma2d<SWAP, 3, false, true, false, 2>(p, nframes, st);     // tensor loads, LDS + STG stores
+    case 6: return launch_yuv420_rgb24_tma2d<SWAP, 3, false, true, true, 3>(p, nframes, st);      // tensor loads (3 stages), tensor stores
+    case 8: return launch_yuv420_rgb24_tma2d<SWAP, 3, false, true, false, 4>(p, nframes, st);     // tensor loads (4 stages), LDS + STG stores
+    default: return launch_yuv420_rgb24_tma2d<SWAP, 3, false, true, false, 3>(p, nframes, st);    // 7: tensor loads (3 stages), LDS + STG stores
+    }
+}
+
+// The automatic form: three-stage tensor-map loads in front of the tier-2 stores, for the 24-bit destinations.
+bool tma_loads_dst(int dstfmt, const FastParams &p, int nframes, cudaStream_t st)
+{
+    switch (dstfmt) {
+    case IMG_RGB24:  return launch_yuv420_rgb24_tma2d<false, 3, false, true, false, 3>(p, nframes, st);
+    case IMG_BGR24:  return launch_yuv420_rgb24_tma2d<true, 3, false, true, false, 3>(p, nframes, st);
+    default: return false;       // 32-bit destinations measured slower this way (read-modify-write of alpha: 0.987 -> 0.938)
     }
 }
 
@@ -1024,6 +1043,22 @@ bool convert_fast(const ConvertArgs &a)
 }
 
 // Tier 3: the same arithmetic, but 24-bit RGB tiles leave shared memory through bulk (TMA) stores.
+// Automatic tier 3: YUV420P -> RGB24 / BGR24 with the planes staged by tensor-map loads (three stages per warp) in front
+// of the tier-2 transposed stores.  Measured against tier 2 in the same run (profiles/r2_tma_tensor_maps.md): 1080p 0.934 ->
+// 0.975 of the copy peak, UHD 0.926 -> 0.958, 720p 0.847 -> 0.879; narrow frames whose rows leave more than a fifth of a
+// block's lanes idle (640 wide: 0.841 -> 0.68) stay on tier 2's flat walk.  Tensor maps need 16-byte strides: w % 32 == 0.
+bool convert_tma_auto(const ConvertArgs &a)
+{
+    static const bool enabled = [] { const char *e = getenv("ACGPU_TMA_AUTO"); return !e || atoi(e) != 0; }();
+    if (!enabled || a.srcfmt != IMG_YUV420P || (a.dstfmt != IMG_RGB24 && a.dstfmt != IMG_BGR24)) return false;
+    FastParams p;
+    if (!fast_domain(a, &p) || p.ragged420 || a.w % 32 || a.h % 2) return false;
+    const int lanes_row = ((p.upr + 31) / 32) * 32;
+    if (p.upr * 10 < lanes_row * 8 || p.upr > 256 * 65535) return false;
+    if (!encode_tiled_fn()) return false;
+    return tma_loads_dst(a.dstfmt, p, a.nframes, a.stream);
+}
+
 bool convert_tma(const ConvertArgs &a)
 {
     if (a.dstfmt != IMG_RGB24 && a.dstfmt != IMG_BGR24) return false;
@@ -1031,7 +1066,7 @@ bool convert_tma(const ConvertArgs &a)
     if (!fast_domain(a, &p) || p.ragged420) return false;
     // $ACGPU_TMA: 0 = bulk stores only (default tier 3), 1 = bulk-async staged loads + LDS/STG stores,
     //             2 = bulk-async staged loads + bulk stores, 3 = 2-D tensor-map stores, 4 = tensor-map loads and stores,
-    //             5 = tensor-map loads + LDS/STG stores, 6 / 7 = as 4 / 5 with a three-stage load pipeline.
+    //             5 = tensor-map loads + LDS/STG stores, 6 / 7 = as 4 / 5 with a three-stage load pipeline, 8 = as 7 with four.
     //             Loads need an even number of units per warp (w % 32 == 0).
     static const int mode = [] { const char *e = getenv("ACGPU_TMA"); return e ? atoi(e) : 0; }();
     if (mode >= 3 && a.srcfmt == IMG_YUV420P && a.w % 32 == 0 && a.h % 2 == 0 && p.upr <= 256 * 65535) {
