@@ -336,7 +336,7 @@ def test_rows_wider_than_one_block(ac, chk):
                    (F.IMG_YUV420P, F.IMG_YUV422P)]:
         src = ck.random_frame(sf, w, h, seed=77)
         got = ac.convert_batch(np.stack([src, src[::-1].copy()]), sf, df, w, h)
-        assert ac.lib.acgpu_last_kernel_tier() == 2
+        assert ac.lib.acgpu_last_kernel_tier() in (2, 3)      # 3: the tensor-map staged form of YUV420P -> RGB24 (segments too)
         assert_same(got[0], chk.convert(src, sf, df, w, h, pad=0)[1], f"wide {F.NAMES[sf]}->{F.NAMES[df]}")
         assert_same(got[1], chk.convert(src[::-1].copy(), sf, df, w, h, pad=0)[1], f"wide {F.NAMES[sf]}->{F.NAMES[df]} #2")
 

@@ -191,19 +191,39 @@ class CopyPool {
     std::mutex m;
     std::condition_variable cv;
     std::vector<Job> q;
+    std::atomic<int> pending{0};
     int nthreads = 0;
 
+    bool try_pop(Job *j)
+    {
+        if (pending.load(std::memory_order_acquire) <= 0) return false;
+        std::lock_guard<std::mutex> lk(m);
+        if (q.empty()) return false;
+        *j = q.back();
+        q.pop_back();
+        pending.fetch_sub(1, std::memory_order_relaxed);
+        return true;
+    }
     void worker()
     {
-        std::unique_lock<std::mutex> lk(m);
         for (;;) {
-            cv.wait(lk, [this] { return !q.empty(); });
-            Job j = q.back();
-            q.pop_back();
-            lk.unlock();
+            Job j{};
+            bool have = false;
+            // chunks of one frame follow each other within microseconds: poll for a while before going to sleep (a
+            // condition-variable wake-up costs more than the 256 KB copy it announces)
+            for (int spin = 0; spin < 4000 && !have; spin++) {
+                have = try_pop(&j);
+                if (!have) __builtin_ia32_pause();
+            }
+            if (!have) {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return !q.empty(); });
+                j = q.back();
+                q.pop_back();
+                pending.fetch_sub(1, std::memory_order_relaxed);
+            }
             memcpy(j.d, j.s, j.n);
             j.left->fetch_sub(1, std::memory_order_release);
-            lk.lock();
         }
     }
 
@@ -234,6 +254,7 @@ public:
         {
             std::lock_guard<std::mutex> lk(m);
             for (int i = 0; i + 1 < pieces; i++) q.push_back(Job{d + (size_t)i * each, s + (size_t)i * each, each, &left});
+            pending.fetch_add(pieces - 1, std::memory_order_release);
         }
         cv.notify_all();
         const size_t done = (size_t)(pieces - 1) * each;
@@ -241,12 +262,7 @@ public:
         while (left.load(std::memory_order_acquire) > 0) {
             // help with whatever is still queued (another caller's pieces count too) instead of spinning idle
             Job j{};
-            bool have = false;
-            {
-                std::lock_guard<std::mutex> lk(m);
-                if (!q.empty()) { j = q.back(); q.pop_back(); have = true; }
-            }
-            if (have) { memcpy(j.d, j.s, j.n); j.left->fetch_sub(1, std::memory_order_release); }
+            if (try_pop(&j)) { memcpy(j.d, j.s, j.n); j.left->fetch_sub(1, std::memory_order_release); }
         }
     }
 };
