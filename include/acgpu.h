@@ -114,9 +114,10 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt,
                                  uint8_t *dest_frames, ImageFormat destfmt,
                                  int width, int height, int nframes);
 /*
- * The same over several GPUs of one host: frames are independent, so the run is cut into `ndevices` contiguous blocks
- * (devices 0 .. ndevices-1; ndevices <= 0 = every visible device) and each block goes through its own device's pipeline
- * on its own internal host thread -- one thread, stream set and staging per device, no exchange between devices.
+ * The same over several GPUs of one host: frames are independent, so the run is shared out among `ndevices` devices
+ * (devices 0 .. ndevices-1; ndevices <= 0 = every visible device) in grains of frames taken from a shared counter -- the
+ * devices of a box do not all get the same share of the host's DMA bandwidth -- and each grain goes through its device's
+ * pipeline on that device's internal host thread: one thread, stream set and staging per device, no exchange between devices.
  * What transcode's N frame threads do by hand (src/frame_threads.c:174-228), for callers that hold a run of frames.
  */
 int acgpu_imgconvert_frames_host_multi(const uint8_t *src_frames, ImageFormat srcfmt,

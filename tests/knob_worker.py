@@ -21,9 +21,12 @@ def main():
     if tier == 0:
         pairs += [(F.IMG_YUV420P, F.IMG_ARGB32), (F.IMG_RGB24, F.IMG_YUV420P), (F.IMG_BGRA32, F.IMG_YV12),
                   (F.IMG_YUV420P, F.IMG_YUV422P), (F.IMG_YUV444P, F.IMG_YUV420P), (F.IMG_UYVY, F.IMG_YUV420P),
-                  (F.IMG_YUV420P, F.IMG_YVYU), (F.IMG_YUV411P, F.IMG_YUV420P), (F.IMG_YUV420P, F.IMG_YUV420P)]
+                  (F.IMG_YUV420P, F.IMG_YVYU), (F.IMG_YUV411P, F.IMG_YUV420P), (F.IMG_YUV420P, F.IMG_YUV420P),
+                  # the row form of the tensor-map staged loads ($ACGPU_TMA_AUTO bits 1 and 2)
+                  (F.IMG_YUV422P, F.IMG_RGB24), (F.IMG_YUV444P, F.IMG_BGR24), (F.IMG_YUV411P, F.IMG_RGB24),
+                  (F.IMG_YUY2, F.IMG_RGB24), (F.IMG_UYVY, F.IMG_BGR24), (F.IMG_YVYU, F.IMG_BGR24)]
     n = 0
-    for (w, h, nf) in [(1920, 16, 2), (720, 36, 3), (1280, 6, 1), (64, 4, 2), (4128, 4, 1)]:
+    for (w, h, nf) in [(1920, 16, 2), (720, 36, 3), (1280, 6, 1), (64, 4, 2), (4128, 4, 1), (4160, 6, 2)]:
         for sf, df in pairs:
             frames = np.stack([ck.random_frame(sf, w, h, seed=70 + i) for i in range(nf)])
             got = ac.convert_batch(frames, sf, df, w, h, prefill=0x33)

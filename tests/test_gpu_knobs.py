@@ -28,6 +28,7 @@ ROOT = os.path.dirname(HERE)
     ({"ACGPU_TMA": "7"}, 3),               # tier 3: three-stage tensor-map loads, LDS + STG stores
     ({"ACGPU_TMA": "8"}, 3),               # tier 3: four-stage tensor-map loads, LDS + STG stores
     ({"ACGPU_TMA_AUTO": "0"}, 0),          # the automatic path without the tensor-map form (tier 2 everywhere)
+    ({"ACGPU_TMA_AUTO": "7"}, 0),          # tensor-map staged loads for EVERY YUV source -> RGB24 / BGR24 (two rows per trip)
 ], ids=lambda v: "-".join(f"{k[6:]}{x}" for k, x in v.items()) if isinstance(v, dict) else f"tier{v}")
 def test_knob_variants_match_the_checker(env, tier):
     e = dict(os.environ)

@@ -86,12 +86,20 @@ __device__ __forceinline__ void stg64_unaligned(uint8_t *p, uint2 v)
     } else if (a == 4) {
         stg32(p, v.x);
         stg32(p + 4, v.y);
-    } else if (!(a & 1)) {
-        uint16_t *h = reinterpret_cast<uint16_t *>(p);
-        h[0] = (uint16_t)v.x; h[1] = (uint16_t)(v.x >> 16); h[2] = (uint16_t)v.y; h[3] = (uint16_t)(v.y >> 16);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) { p[i] = (uint8_t)(v.x >> (8 * i)); p[4 + i] = (uint8_t)(v.y >> (8 * i)); }
+    } else if (!(a & 1)) {              // 2 mod 4: 2 + 4 + 2 bytes
+        *reinterpret_cast<uint16_t *>(p) = (uint16_t)v.x;
+        stg32(p + 2, __funnelshift_r(v.x, v.y, 16));
+        *reinterpret_cast<uint16_t *>(p + 6) = (uint16_t)(v.y >> 16);
+    } else if ((a & 3) == 1) {          // 1 mod 4: 1 + 2 + 4 + 1 bytes
+        p[0] = (uint8_t)v.x;
+        *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(v.x >> 8);
+        stg32(p + 3, __funnelshift_r(v.x, v.y, 24));
+        p[7] = (uint8_t)(v.y >> 24);
+    } else {                            // 3 mod 4: 1 + 4 + 2 + 1 bytes
+        p[0] = (uint8_t)v.x;
+        stg32(p + 1, __funnelshift_r(v.x, v.y, 8));
+        *reinterpret_cast<uint16_t *>(p + 5) = (uint16_t)(v.y >> 8);
+        p[7] = (uint8_t)(v.y >> 24);
     }
 }
 // bytes j0 .. j0+nb-1 of v to p[0 .. nb)

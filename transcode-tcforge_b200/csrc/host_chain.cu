@@ -15,6 +15,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -414,10 +415,13 @@ DeviceWorker *g_workers[kMaxDev];
 
 }  // namespace
 
-// Frames are independent: a run of host frames is cut into contiguous blocks, one per device, and every
-// block goes through that device's own pipeline on its own long-lived host thread (created on first use, parked on a
-// condition variable: streams, pipeline buffers and device contexts persist from call to call).  No exchange between
-// devices, no collective.  job(device, first_frame, end_frame) runs on the device's thread with that device selected.
+// Frames are independent: a run of host frames is shared out among the devices, each served by its own
+// long-lived host thread (created on first use, parked on a condition variable: streams, pipeline buffers and device
+// contexts persist from call to call).  No exchange between devices, no collective.  The devices of one box do not all get
+// the same share of the host's DMA bandwidth (profiles/r2_host_dma_probe_8gpu.md: four GPUs at half the rate of the other
+// four when all eight copy), so the run is not cut into equal blocks: every device thread takes the next grain of frames
+// from a shared counter until none are left.  job(device, first_frame, end_frame) runs on the device's thread with that
+// device selected.
 int run_on_devices(const char *who, int ndevices, int nframes, const std::function<bool(int, int, int)> &job)
 {
     int visible = 0;
@@ -426,15 +430,21 @@ int run_on_devices(const char *who, int ndevices, int nframes, const std::functi
     if (ndevices > visible || ndevices > kMaxDev) { set_error("%s: %d devices requested, %d visible", who, ndevices, visible); return 0; }
     if (nframes <= 0) return 1;
     if (ndevices > nframes) ndevices = nframes;
+    // a grain is one pipelined call: long enough to amortise the pipeline's fill and drain, short enough to balance
+    int grain = nframes / (ndevices * 6);
+    if (grain < 16) grain = 16;
+    if (grain > (nframes + ndevices - 1) / ndevices) grain = (nframes + ndevices - 1) / ndevices;
     std::lock_guard<std::mutex> call(g_multi_mutex);
     std::vector<int> ok((size_t)ndevices, 0);
     std::vector<std::string> why((size_t)ndevices);
+    std::atomic<int> next{0};
     for (int d = 0; d < ndevices; d++) {
         if (!g_workers[d]) g_workers[d] = new DeviceWorker();
-        const int f0 = (int)((int64_t)nframes * d / ndevices), f1 = (int)((int64_t)nframes * (d + 1) / ndevices);
-        g_workers[d]->submit([=, &ok, &why, &job] {
-            ok[(size_t)d] = acgpu_set_device(d) && job(d, f0, f1);
-            if (!ok[(size_t)d]) why[(size_t)d] = tls.err;
+        g_workers[d]->submit([=, &ok, &why, &job, &next] {
+            bool good = acgpu_set_device(d) == 1;
+            for (int f0; good && (f0 = next.fetch_add(grain)) < nframes;) good = job(d, f0, f0 + grain < nframes ? f0 + grain : nframes);
+            ok[(size_t)d] = good;
+            if (!good) why[(size_t)d] = tls.err;
         });
     }
     for (int d = 0; d < ndevices; d++) g_workers[d]->wait();

@@ -825,6 +825,110 @@ __global__ void __launch_bounds__(256, 3) k_yuv420_rgb24_tma2d(FastParams p, con
     if (TSTORE && lane == 0) bulk_wait_all<0>();
 }
 
+// The same front end for the other YUV sources (4:2:2, 4:4:4, 4:1:1 planar; YUY2 / UYVY / YVYU packed) -> RGB24 / BGR24:
+// a warp takes 512 pixels of TWO consecutive rows per trip (every plane's box is two rows high, so a trip is three tensor
+// loads for planar sources and one for packed ones), converts each row as tier 2's linear walk does and stores through
+// the tier-2 transpose.  Stage layout: luma 2 x 512 bytes, then U and V with 2 x kCRow bytes each; packed: 2 x 1024 bytes.
+template <int SRC> struct RowStage {
+    static constexpr bool packed = SrcInfo<SRC>::packed;
+    static constexpr int kCRow = SRC == S444 ? 512 : SRC == S411 ? 128 : 256;       // chroma bytes of one plane, one row, one warp
+    static constexpr int kBytes = packed ? 2048 : 1024 + 4 * kCRow;
+};
+
+template <int SRC, bool SWAP, int STAGES>
+__global__ void __launch_bounds__(256, 2) k_yuvrows_rgb24_tma(FastParams p, const __grid_constant__ CUtensorMap mapY,
+                                                              const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapV)
+{
+    constexpr int BPP = 3;
+    using SI = SrcInfo<SRC>;
+    using RS = RowStage<SRC>;
+    __shared__ int2 s_tab[512];
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    constexpr int kPerWarp = 1536 + STAGES * RS::kBytes + 128;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs16)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wbase = s_raw + (size_t)warp * kPerWarp;
+    uint4 *stage_out = reinterpret_cast<uint4 *>(wbase);
+    uint8_t *in0 = wbase + 1536;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + kPerWarp - 128);
+    const int frame = blockIdx.y;
+    const size_t doff = (size_t)frame * p.dpitch;
+    const int wu0 = blockIdx.z * blockDim.x + warp * 32;
+    const int nvalid = min(32, p.upr - wu0);
+    if (nvalid <= 0) return;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int rp, int st) {       // lane 0 only
+        uint8_t *b = in0 + st * RS::kBytes;
+        mbar_expect_tx(&bars[st], RS::kBytes);
+        if (RS::packed) {
+            tensor_load_3d(b, &mapY, wu0 * 8, 2 * rp, frame, &bars[st]);               // 16 pixels = 32 bytes = 8 words
+        } else {
+            tensor_load_3d(b, &mapY, wu0 * 4, 2 * rp, frame, &bars[st]);
+            tensor_load_3d(b + 1024, &mapU, wu0 * (RS::kCRow / 128), 2 * rp, frame, &bars[st]);
+            tensor_load_3d(b + 1024 + 2 * RS::kCRow, &mapV, wu0 * (RS::kCRow / 128), 2 * rp, frame, &bars[st]);
+        }
+    };
+    const int step = (int)gridDim.x;
+    int rp = blockIdx.x;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++)
+            if (rp + s * step < p.nrp) issue(rp + s * step, s);
+    }
+    for (int it = 0; rp < p.nrp; rp += step, it++) {
+        const int st = it % STAGES;
+        if (lane == 0 && rp + (STAGES - 1) * step < p.nrp) issue(rp + (STAGES - 1) * step, (it + STAGES - 1) % STAGES);
+        mbar_wait(&bars[st], (it / STAGES) & 1);
+        const uint8_t *b = in0 + st * RS::kBytes;
+        uint32_t yw[2][SI::packed ? 8 : 4], cu[2][4], cv[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (RS::packed) {
+                const uint4 a = reinterpret_cast<const uint4 *>(b + r * 1024)[2 * lane], c = reinterpret_cast<const uint4 *>(b + r * 1024)[2 * lane + 1];
+                yw[r][0] = a.x; yw[r][1] = a.y; yw[r][2] = a.z; yw[r][3] = a.w;
+                yw[r][4] = c.x; yw[r][5] = c.y; yw[r][6] = c.z; yw[r][7] = c.w;
+            } else {
+                const uint4 a = reinterpret_cast<const uint4 *>(b + r * 512)[lane];
+                yw[r][0] = a.x; yw[r][1] = a.y; yw[r][2] = a.z; yw[r][3] = a.w;
+                const uint8_t *ub = b + 1024 + r * RS::kCRow, *vb = ub + 2 * RS::kCRow;
+                if (SRC == S444) {
+                    const uint4 u4 = reinterpret_cast<const uint4 *>(ub)[lane], v4 = reinterpret_cast<const uint4 *>(vb)[lane];
+                    cu[r][0] = u4.x; cu[r][1] = u4.y; cu[r][2] = u4.z; cu[r][3] = u4.w;
+                    cv[r][0] = v4.x; cv[r][1] = v4.y; cv[r][2] = v4.z; cv[r][3] = v4.w;
+                } else if (SRC == S422) {
+                    const uint2 u2 = reinterpret_cast<const uint2 *>(ub)[lane], v2 = reinterpret_cast<const uint2 *>(vb)[lane];
+                    cu[r][0] = u2.x; cu[r][1] = u2.y; cv[r][0] = v2.x; cv[r][1] = v2.y;
+                } else {
+                    cu[r][0] = reinterpret_cast<const uint32_t *>(ub)[lane];
+                    cv[r][0] = reinterpret_cast<const uint32_t *>(vb)[lane];
+                }
+            }
+        }
+        __syncwarp();        // every lane has read this stage before lane 0 may refill it (STAGES - 1 trips from now)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            int cr[SI::nchroma], cg[SI::nchroma], cb[SI::nchroma];
+#pragma unroll
+            for (int s = 0; s < SI::nchroma; s++) {
+                uint32_t U, V;
+                if (RS::packed) { U = byte_of(yw[r][s], SI::uo); V = byte_of(yw[r][s], SI::vo); }
+                else { U = byte_of(cu[r][s >> 2], s & 3); V = byte_of(cv[r][s >> 2], s & 3); }
+                chroma_terms<SRC>(s_tab, U, V, cr[s], cg[s], cb[s]);
+            }
+            uint32_t ow[12];
+            convert_row<SRC, SWAP, BPP, false>(yw[r], cr, cg, cb, ow);
+            uint8_t *row = p.d0 + doff + ((size_t)(2 * rp + r) * p.w + (size_t)wu0 * 16) * BPP;
+            store_row_rgb<BPP, false>(stage_out, lane, ow, row, nvalid);
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1043,20 +1147,73 @@ bool convert_fast(const ConvertArgs &a)
 }
 
 // Tier 3: the same arithmetic, but 24-bit RGB tiles leave shared memory through bulk (TMA) stores.
+template <int SRC, bool SWAP>
+bool launch_yuvrows_rgb24_tma(const FastParams &p0, int nframes, cudaStream_t st)
+{
+    using RS = RowStage<SRC>;
+    constexpr int STAGES = 3;
+    FastParams p = p0;
+    p.upr = p.w / 16;
+    p.nrp = p.h / 2;
+    CUtensorMap mY, mU, mV;
+    const uint64_t w = (uint64_t)p.w, h = (uint64_t)p.h, nf = (uint64_t)nframes;
+    if (RS::packed) {
+        if (!make_map3(&mY, p.s0, 4, w * 2, h, nf, p.spitch, 256, 2)) return false;
+        mU = mV = mY;
+    } else {
+        const uint64_t crow = SRC == S444 ? w : SRC == S411 ? w / 4 : w / 2;
+        if (!make_map3(&mY, p.s0, 4, w, h, nf, p.spitch, 128, 2) || !make_map3(&mU, p.s1, 4, crow, h, nf, p.spitch, RS::kCRow / 4, 2)
+            || !make_map3(&mV, p.s2, 4, crow, h, nf, p.spitch, RS::kCRow / 4, 2))
+            return false;
+    }
+    const LaunchShape s = shape_420(p.upr, p.nrp, nframes, 8);
+    const size_t smem = (size_t)(s.block.x / 32) * (1536 + STAGES * RS::kBytes + 128) + 128;
+    auto kern = k_yuvrows_rgb24_tma<SRC, SWAP, STAGES>;
+    if (!check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return false;
+    kern<<<s.grid, s.block, smem, st>>>(p, mY, mU, mV);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_yuvrows_rgb24_tma");
+    return true;
+}
+
+template <int SRC>
+bool tma_rows_dst(int dstfmt, const FastParams &p, int nframes, cudaStream_t st)
+{
+    return dstfmt == IMG_BGR24 ? launch_yuvrows_rgb24_tma<SRC, true>(p, nframes, st) : launch_yuvrows_rgb24_tma<SRC, false>(p, nframes, st);
+}
+
 // Automatic tier 3: YUV420P -> RGB24 / BGR24 with the planes staged by tensor-map loads (three stages per warp) in front
 // of the tier-2 transposed stores.  Measured against tier 2 in the same run (profiles/r2_tma_tensor_maps.md): 1080p 0.934 ->
 // 0.975 of the copy peak, UHD 0.926 -> 0.958, 720p 0.847 -> 0.879; narrow frames whose rows leave more than a fifth of a
 // block's lanes idle (640 wide: 0.841 -> 0.68) stay on tier 2's flat walk.  Tensor maps need 16-byte strides: w % 32 == 0.
 bool convert_tma_auto(const ConvertArgs &a)
 {
-    static const bool enabled = [] { const char *e = getenv("ACGPU_TMA_AUTO"); return !e || atoi(e) != 0; }();
-    if (!enabled || a.srcfmt != IMG_YUV420P || (a.dstfmt != IMG_RGB24 && a.dstfmt != IMG_BGR24)) return false;
+    // bit 0: 4:2:0; bit 1: 4:1:1 and wide 4:2:2 (the sources the row form wins on); bit 2: every other YUV source (measured
+    // slower than tier 2: selectable for experiments and parity tests only)
+    static const int enabled = [] { const char *e = getenv("ACGPU_TMA_AUTO"); return e ? atoi(e) : 3; }();
+    if (!enabled || (a.dstfmt != IMG_RGB24 && a.dstfmt != IMG_BGR24)) return false;
+    const FmtDesc sd = describe(a.srcfmt);
+    if (sd.kind != K_PLANAR && sd.kind != K_PACKED) return false;
     FastParams p;
-    if (!fast_domain(a, &p) || p.ragged420 || a.w % 32 || a.h % 2) return false;
-    const int lanes_row = ((p.upr + 31) / 32) * 32;
-    if (p.upr * 10 < lanes_row * 8 || p.upr > 256 * 65535) return false;
+    if (!fast_domain(a, &p) || p.ragged420 || a.h % 2) return false;
+    // tensor-map strides are multiples of 16 bytes: the narrowest plane's rows decide
+    const int wmod = a.srcfmt == IMG_YUV411P ? 64 : sd.kind == K_PACKED || a.srcfmt == IMG_YUV444P ? 16 : 32;
+    if (a.w % wmod) return false;
+    const int upr = a.w / 16, lanes_row = ((upr + 31) / 32) * 32;
+    if (upr * 10 < lanes_row * 8 || upr > 256 * 65535) return false;
     if (!encode_tiled_fn()) return false;
-    return tma_loads_dst(a.dstfmt, p, a.nframes, a.stream);
+    if (a.srcfmt == IMG_YUV420P) return (enabled & 1) && tma_loads_dst(a.dstfmt, p, a.nframes, a.stream);
+    const bool wins = a.srcfmt == IMG_YUV411P || (a.srcfmt == IMG_YUV422P && a.w >= 1920);
+    if (!(enabled & (wins ? 2 : 4))) return false;
+    switch (a.srcfmt) {
+    case IMG_YUV422P: return tma_rows_dst<S422>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV444P: return tma_rows_dst<S444>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV411P: return tma_rows_dst<S411>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUY2:    return tma_rows_dst<SYUY2>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_UYVY:    return tma_rows_dst<SUYVY>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YVYU:    return tma_rows_dst<SYVYU>(a.dstfmt, p, a.nframes, a.stream);
+    default: return false;
+    }
 }
 
 bool convert_tma(const ConvertArgs &a)

@@ -46,27 +46,6 @@ __device__ __forceinline__ uint4 ld16_any(const uint8_t *p)
     return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
 
-// `need` (1..16) bytes from any address in the low bytes of the result; only the aligned 16-byte blocks that hold needed
-// bytes are touched, so the access never leaves the plane.
-__device__ __forceinline__ uint4 ld16_upto(const uint8_t *p, uint32_t need)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint4 *q = reinterpret_cast<const uint4 *>(a & ~(uintptr_t)15);
-    const uint32_t ofs = (uint32_t)(a & 15);
-    const uint4 lo = __ldg(q);
-    if (ofs == 0) return lo;
-    const uint4 hi = ofs + need > 16 ? __ldg(q + 1) : make_uint4(0, 0, 0, 0);
-    const uint32_t sh = (ofs & 3) * 8;
-    uint32_t w0, w1, w2, w3, w4;
-    switch (ofs >> 2) {
-    case 0:  w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
-    case 1:  w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
-    case 2:  w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
-    default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
-    }
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Window copy: destination row y shows bytes [sxb, sxb + cn) of source row y*row_mul + row_add at its bytes
 // [cl, cl + cn) and `fill` everywhere else (and in every row whose source row falls outside the source).
@@ -102,40 +81,15 @@ __device__ __forceinline__ int window_chunk(const TcvWindow &p, const uint8_t *s
             return 1;
         }
     }
-    // mixed chunk (a border or a row end inside it): at most two row pieces, each a run of fill bytes, a run of copied
-    // bytes and a run of fill bytes.  The copied run is fetched with ONE bounded 16-byte load, shifted to its place in the
-    // chunk and merged under a byte mask (it used to be sixteen predicated byte loads: one such chunk per destination row
-    // when rows are not multiples of 16 bytes, and the whole warp waited for it).
-    uint32_t w[4] = {p.fill, p.fill, p.fill, p.fill};
-    uint32_t yy = y, xx = xb, pos = 0;                      // pos: chunk byte where the current row piece starts
-    while (pos < 16) {
-        const uint32_t len = min(16u - pos, p.dBpl - xx);   // bytes of this chunk that lie in row yy
-        const int sr = (int)yy * p.row_mul + p.row_add;
-        if (sr >= 0 && sr < p.srows) {
-            // copied columns of the row piece [xx, xx + len) are those inside [cl, cl + cn)
-            const uint32_t a = max(xx, p.cl), b = min(xx + len, p.cl + p.cn);
-            if (a < b) {
-                const uint32_t c0 = pos + (a - xx), c1 = pos + (b - xx);          // chunk bytes [c0, c1) are copied
-                const uint4 v4 = ld16_upto(src + (size_t)sr * p.sBpl + p.sxb + (a - p.cl), c1 - c0);
-                const uint32_t s[4] = {v4.x, v4.y, v4.z, v4.w};
-                const uint32_t ws = c0 >> 2, bs = (c0 & 3) * 8;
+    // mixed chunk (border / row end inside it): walk its 16 bytes with a running (row, column)
+    uint32_t w[4] = {0, 0, 0, 0}, yy = y, xx = xb;
+    int sr = (int)yy * p.row_mul + p.row_add;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    // data word k of the chunk = source bytes shifted up by c0: words ws back, then bs bits
-                    const int hi = k - (int)ws, lo = hi - 1;
-                    const uint32_t vh = hi >= 0 ? (hi == 0 ? s[0] : hi == 1 ? s[1] : hi == 2 ? s[2] : s[3]) : 0u;
-                    const uint32_t vl = lo >= 0 ? (lo == 0 ? s[0] : lo == 1 ? s[1] : lo == 2 ? s[2] : s[3]) : 0u;
-                    const uint32_t data = __funnelshift_l(vl, vh, bs);
-                    const int l = max(0, min(4, (int)c0 - 4 * k)), h = max(0, min(4, (int)c1 - 4 * k));
-                    const uint32_t mh = h == 4 ? 0xFFFFFFFFu : (1u << (8 * h)) - 1u, ml = l == 4 ? 0xFFFFFFFFu : (1u << (8 * l)) - 1u;
-                    const uint32_t m = mh & ~ml;
-                    w[k] = (w[k] & ~m) | (data & m);
-                }
-            }
-        }
-        pos += len;
-        xx = 0;
-        yy++;
+    for (int i = 0; i < 16; i++) {
+        uint32_t b = p.fill & 0xFFu;
+        if (sr >= 0 && sr < p.srows && xx >= p.cl && xx < p.cl + p.cn) b = __ldg(src + (size_t)sr * p.sBpl + p.sxb + (xx - p.cl));
+        w[i >> 2] |= b << (8 * (i & 3));
+        if (++xx == p.dBpl) { xx = 0; yy++; sr += p.row_mul; }
     }
     v = make_uint4(w[0], w[1], w[2], w[3]);
     return 1;
