@@ -276,9 +276,10 @@ def test_chain_rejections(ac):
     buf.free()
 
 
-@pytest.mark.parametrize("budget", [1, 4_000_000, 9_000_000])
-def test_chain_batch_walks_sub_batches_when_the_temporary_is_small(budget):
-    """7 frames of 640x480 with room for 1, 2 and 4 frames per sub-batch (the last one partial)."""
+@pytest.mark.parametrize("budget,fuse", [(1, 1), (4_000_000, 0), (9_000_000, 1), (1 << 31, 0)])
+def test_chain_batch_walks_sub_batches_when_the_temporary_is_small(budget, fuse):
+    """7 frames of 640x480 with room for 1, 2, 4 and all frames per sub-batch (the last one partial), with and without the
+    fused form of conversion pairs ($ACGPU_CHAIN_FUSE)."""
     import os
     import subprocess
     import sys
@@ -286,6 +287,7 @@ def test_chain_batch_walks_sub_batches_when_the_temporary_is_small(budget):
     root = os.path.dirname(here)
     e = dict(os.environ)
     e["ACGPU_CHAIN_SCRATCH_BYTES"] = str(budget)
+    e["ACGPU_CHAIN_FUSE"] = str(fuse)
     e["PYTHONPATH"] = os.pathsep.join([root, here, e.get("PYTHONPATH", "")])
     r = subprocess.run([sys.executable, os.path.join(here, "chain_worker.py")], capture_output=True, text=True, env=e, cwd=root, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().startswith("OK"), (r.stdout[-400:], r.stderr[-400:])

@@ -55,6 +55,10 @@ bool convert_tma(const ConvertArgs &a);
 // false without launching when the call is outside its domain.
 bool convert_tma_auto(const ConvertArgs &a);
 
+// Fused YUV420P -> RGB (any layout, never materialised) -> YUV420P / 422P / 444P for frame chains (kernels_fast.cu);
+// a.src / a.dst are the outer batches.  false (no launch, no error) when outside its domain.
+bool convert_fused_yuv420_rgb_yuv(const ConvertArgs &a);
+
 // Fused RGB24 -> gray -> RGB24 in place (kernels_fast_rgb.cu); false when outside the vectorised domain.
 bool decolor_rgb24_fast(uint8_t *frames, size_t pitch, int w, int h, int nframes, cudaStream_t st);
 

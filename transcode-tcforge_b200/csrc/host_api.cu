@@ -73,6 +73,16 @@ bool bind_device()
 
 bool process_exiting() { return g_exiting.load(); }
 
+int pipe_slots()
+{
+    static const int n = [] {
+        const char *e = getenv("ACGPU_PIPE_SLOTS");
+        const int v = e ? atoi(e) : 3;
+        return v < 2 ? 2 : v > kPipeSlots ? kPipeSlots : v;
+    }();
+    return n;
+}
+
 DevCtx *ctx()
 {
     if (!bind_device()) return nullptr;
@@ -976,7 +986,7 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
     if (per < 1) per = 1;
     if (per > (size_t)nframes) per = nframes;
     const size_t slot_bytes = per * (sp + dp);
-    for (int s = 0; s < kPipeSlots; s++) {
+    for (int s = 0; s < pipe_slots(); s++) {
         if (!c->pipe_stream[s] && !check(cudaStreamCreateWithFlags(&c->pipe_stream[s], cudaStreamNonBlocking), "pipe stream")) return 0;
         if (c->pipe_cap[s] < slot_bytes) {
             if (c->pipe_buf[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaFree(c->pipe_buf[s]); c->pipe_buf[s] = nullptr; c->pipe_cap[s] = 0; }
@@ -986,7 +996,7 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
     }
     int chunk = 0;
     for (int f0 = 0; f0 < nframes; f0 += (int)per, chunk++) {
-        const int s = chunk % kPipeSlots;
+        const int s = chunk % pipe_slots();
         const int n = nframes - f0 < (int)per ? nframes - f0 : (int)per;
         cudaStream_t st = c->pipe_stream[s];
         uint8_t *dsrc = c->pipe_buf[s], *ddst = dsrc + per * sp;
@@ -998,7 +1008,7 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
         if (!acgpu_imgconvert_batch(sp3, srcfmt, sp, dp3, destfmt, dp, width, height, n, reinterpret_cast<acgpu_stream_t>(st))) return 0;
         if (!check(cudaMemcpy2DAsync(dest_frames + (size_t)f0 * dfb, dfb, ddst, dp, dfb, n, cudaMemcpyDeviceToHost, st), "D2H frames")) return 0;
     }
-    for (int s = 0; s < kPipeSlots; s++)
+    for (int s = 0; s < pipe_slots(); s++)
         if (!check(cudaStreamSynchronize(c->pipe_stream[s]), "acgpu_imgconvert_frames_host")) return 0;
     return 1;
 }

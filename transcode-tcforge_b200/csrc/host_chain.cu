@@ -315,9 +315,9 @@ bool run_chain(DevCtx *c, acgpu_stream_t as, const Plan &pl, const acgpu_chain_o
     cudaStream_t st = pick_stream(c, as);
     Buf cur = in;
     bool cur_mutable = in_mutable;
-    int toggle = 0;
     int outs_left = pl.n_out;
-    auto next_scratch = [&]() { Buf b = toggle ? s1 : s0; toggle ^= 1; if (b.p == cur.p) { b = toggle ? s1 : s0; toggle ^= 1; } return b; };
+    auto next_scratch = [&]() { return cur.p == s0.p ? s1 : s0; };       // the scratch buffer the current frame is not in
+    static const bool fuse = [] { const char *e = getenv("ACGPU_CHAIN_FUSE"); return !e || atoi(e) != 0; }();
     auto copy_to = [&](Buf to, const Geo &g) {
         return check(cudaMemcpy2DAsync(to.p, to.pitch, cur.p, cur.pitch, geo_bytes(g), (size_t)nf, cudaMemcpyDeviceToDevice, st), "chain copy");
     };
@@ -334,6 +334,29 @@ bool run_chain(DevCtx *c, acgpu_stream_t as, const Plan &pl, const acgpu_chain_o
             Buf tmp = cur.p == s0.p ? s1 : s0;
             if (!run_in_place_stage(c, as, ops[k], gi, cur, tmp, nf)) return false;
             continue;
+        }
+        // Two conversions through an RGB frame nobody looks at (YUV420P -> RGB -> planar YUV: BASELINE config 4, the filter
+        // wrappers' round trip with nothing in between) are one fused pass when the geometry allows it.
+        if (fuse && k + 1 < nops && ops[k].kind == ACGPU_CHAIN_CONVERT && ops[k + 1].kind == ACGPU_CHAIN_CONVERT && gi.fmt == IMG_YUV420P
+            && describe(ops[k].p[0]).kind == K_RGB && !stage_noop(ops[k + 1], go)) {
+            const Geo &g2 = pl.geo[(size_t)k + 2];
+            Buf to2 = (outs_left - 2 == 0 && out.p) ? out : next_scratch();
+            ConvertArgs a{};
+            a.srcfmt = IMG_YUV420P; a.dstfmt = g2.fmt; a.w = gi.w; a.h = gi.h; a.nframes = nf; a.stream = st;
+            a.src.p[0] = cur.p; a.src.p[1] = cur.p + (size_t)gi.w * gi.h; a.src.p[2] = a.src.p[1] + chroma_plane_bytes(IMG_YUV420P, gi.w, gi.h);
+            a.src.pitch = cur.pitch;
+            a.dst.p[0] = to2.p; a.dst.p[1] = to2.p + (size_t)g2.w * g2.h; a.dst.p[2] = a.dst.p[1] + chroma_plane_bytes(g2.fmt, g2.w, g2.h);
+            a.dst.pitch = to2.pitch;
+            tls.err[0] = 0;
+            if (convert_fused_yuv420_rgb_yuv(a)) {
+                tls.last_tier = 2;
+                outs_left -= 2;
+                cur = to2;
+                cur_mutable = true;
+                k++;                      // both stages done
+                continue;
+            }
+            if (tls.err[0]) return false;     // a launch failed (outside the fused domain it returns false silently)
         }
         outs_left--;
         const bool to_out = outs_left == 0 && out.p;
@@ -558,7 +581,7 @@ int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int widt
     if (per < 1) per = 1;
     if (per > (size_t)nframes) per = (size_t)nframes;
     const size_t slot_bytes = per * (ip + (preload ? 3 : 2) * tp);
-    for (int s = 0; s < kPipeSlots; s++) {
+    for (int s = 0; s < pipe_slots(); s++) {
         if (!c->pipe_stream[s] && !check(cudaStreamCreateWithFlags(&c->pipe_stream[s], cudaStreamNonBlocking), "pipe stream")) return 0;
         if (c->pipe_cap[s] < slot_bytes) {
             if (c->pipe_buf[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaFree(c->pipe_buf[s]); c->pipe_buf[s] = nullptr; c->pipe_cap[s] = 0; }
@@ -568,7 +591,7 @@ int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int widt
     }
     int chunk = 0;
     for (int f0 = 0; f0 < nframes; f0 += (int)per, chunk++) {
-        const int s = chunk % kPipeSlots;
+        const int s = chunk % pipe_slots();
         const int n = nframes - f0 < (int)per ? nframes - f0 : (int)per;
         cudaStream_t st = c->pipe_stream[s];
         acgpu_stream_t as = reinterpret_cast<acgpu_stream_t>(st);
@@ -582,7 +605,7 @@ int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int widt
         if (!run_chain(c, as, pl, ops, nops, in, true, s0, s1, out, n, &res)) return 0;
         if (!check(cudaMemcpy2DAsync(dest_frames + (size_t)f0 * outb, outb, res.p, res.pitch, outb, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H frames")) return 0;
     }
-    for (int s = 0; s < kPipeSlots; s++)
+    for (int s = 0; s < pipe_slots(); s++)
         if (!check(cudaStreamSynchronize(c->pipe_stream[s]), "acgpu_chain_frames_host")) return 0;
     return 1;
 }

@@ -12,7 +12,8 @@
 namespace acgpu {
 
 constexpr int kMaxDev = 16;
-constexpr int kPipeSlots = 3;
+constexpr int kPipeSlots = 6;          // buffers of the host-frame pipelines; pipe_slots() of them are used
+int pipe_slots();                      // $ACGPU_PIPE_SLOTS, default 3
 
 struct Blob {               // small device-resident tables cached by content (row-op lists, weights)
     uint64_t hash;
@@ -36,9 +37,9 @@ struct DevCtx {
     cudaEvent_t ring_ev[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};   // slot's last DMA (either direction) is done
     int      ring_next = 0;
     std::vector<Blob> blobs;
-    cudaStream_t pipe_stream[kPipeSlots] = {nullptr, nullptr, nullptr};
-    uint8_t *pipe_buf[kPipeSlots] = {nullptr, nullptr, nullptr};
-    size_t   pipe_cap[kPipeSlots] = {0, 0, 0};
+    cudaStream_t pipe_stream[kPipeSlots] = {};
+    uint8_t *pipe_buf[kPipeSlots] = {};
+    size_t   pipe_cap[kPipeSlots] = {};
 };
 
 bool process_exiting();      // true once exit() has begun: destructors then leave CUDA alone

@@ -1074,6 +1074,74 @@ bool fast_rgb2yuv(const ConvertArgs &a, const FastParams &p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused YUV420P -> RGB -> YUV (frame chains, BASELINE config 4: YUV420P -> RGB24 -> YUV422P).  Two conversions through an
+// RGB frame that nobody looks at are one pass: the 8-bit RGB values of a pixel are formed in registers exactly as
+// k_yuv2rgb forms them (same table terms, same clamp; convert_row in its 32-bit layout gives one word per pixel) and fed
+// straight to the dp2a accumulators of k_rgb2yuv.  The intermediate's byte order does not matter -- the second conversion
+// reads the channels it was written with -- so every RGB layout fuses to the same code.  Bit-identical to the two calls;
+// 3.5 bytes of HBM traffic per pixel instead of 9.5.
+template <int DST>
+__global__ void __launch_bounds__(256, 3) k_yuv420_rgb_yuv(FastParams p)
+{
+    __shared__ int2 s_tab[512];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs16)[i];
+    __syncthreads();
+    const size_t soff = (size_t)blockIdx.y * p.spitch, doff = (size_t)blockIdx.y * p.dpitch;
+    const uint8_t *Ys = p.s0 + soff, *Us = p.s1 + soff, *Vs = p.s2 + soff;
+    uint8_t *Y = p.d0 + doff, *U = p.d1 + doff, *V = p.d2 + doff;
+    const int unit = blockIdx.z * blockDim.x + threadIdx.x;
+    if (unit >= p.upr) return;
+    constexpr int SL = L_RGBA;          // convert_row<..., 4, false>: R, G, B in bytes 0..2 of each pixel word
+    for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
+        const uint8_t *yp = Ys + (size_t)(2 * rp) * p.w + unit * 16;
+        const uint4 a = ldg128(yp), b = ldg128(yp + p.w);
+        const size_t co = (size_t)rp * (p.w >> 1) + unit * 8;
+        const uint2 uu = ldg64(Us + co), vv = ldg64(Vs + co);
+        int cr[8], cg[8], cb[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            chroma_terms<S420>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t yw[4] = {r ? b.x : a.x, r ? b.y : a.y, r ? b.z : a.z, r ? b.w : a.w};
+            uint32_t px[16], ay[16];
+            convert_row<S420, false, 4, false>(yw, cr, cg, cb, px);
+#pragma unroll
+            for (int k = 0; k < 16; k++) ay[k] = acc_y<SL>(px[k]);
+            const size_t row = (size_t)(2 * rp + r);
+            stg128(Y + row * p.w + unit * 16,
+                   make_uint4(pack_b2x4(ay[0], ay[1], ay[2], ay[3]), pack_b2x4(ay[4], ay[5], ay[6], ay[7]),
+                              pack_b2x4(ay[8], ay[9], ay[10], ay[11]), pack_b2x4(ay[12], ay[13], ay[14], ay[15])));
+            if (DST == D422) {          // U at even x, V at odd x of every row (img_yuv_rgb.c:166)
+                uint32_t ua[8], va[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { ua[k] = acc_u<SL>(px[2 * k]); va[k] = acc_v<SL>(px[2 * k + 1]); }
+                stg64(U + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[1], ua[2], ua[3]), pack_b2x4(ua[4], ua[5], ua[6], ua[7])));
+                stg64(V + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[0], va[1], va[2], va[3]), pack_b2x4(va[4], va[5], va[6], va[7])));
+            } else if (DST == D420) {   // U at (even x, even y), V at (odd x, odd y) (:162)
+                uint32_t ca[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) ca[k] = r ? acc_v<SL>(px[2 * k + 1]) : acc_u<SL>(px[2 * k]);
+                stg64((r ? V : U) + (size_t)rp * (p.w >> 1) + unit * 8,
+                      make_uint2(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7])));
+            } else {                    // D444: every pixel
+                uint32_t ca[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) ca[k] = acc_u<SL>(px[k]);
+                stg128(U + row * p.w + unit * 16,
+                       make_uint4(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7]),
+                                  pack_b2x4(ca[8], ca[9], ca[10], ca[11]), pack_b2x4(ca[12], ca[13], ca[14], ca[15])));
+#pragma unroll
+                for (int k = 0; k < 16; k++) ca[k] = acc_v<SL>(px[k]);
+                stg128(V + row * p.w + unit * 16,
+                       make_uint4(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7]),
+                                  pack_b2x4(ca[8], ca[9], ca[10], ca[11]), pack_b2x4(ca[12], ca[13], ca[14], ca[15])));
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // Builds the launch parameters if the call is inside the vectorised tiers' domain.
@@ -1214,6 +1282,27 @@ bool convert_tma_auto(const ConvertArgs &a)
     case IMG_YVYU:    return tma_rows_dst<SYVYU>(a.dstfmt, p, a.nframes, a.stream);
     default: return false;
     }
+}
+
+// YUV420P -> (any RGB layout) -> YUV420P / YUV422P / YUV444P in one pass.  `a` describes the OUTER pair: a.src is the
+// YUV420P batch, a.dst the final YUV batch.  Returns false without launching when outside the fused kernel's domain
+// (the chain then runs the two conversions).
+bool convert_fused_yuv420_rgb_yuv(const ConvertArgs &a)
+{
+    if (a.srcfmt != IMG_YUV420P || (a.dstfmt != IMG_YUV422P && a.dstfmt != IMG_YUV420P && a.dstfmt != IMG_YUV444P)) return false;
+    FastParams p;
+    if (!fast_domain(a, &p) || p.ragged420 || a.h % 2) return false;
+    p.upr = a.w / 16;
+    p.nrp = a.h / 2;
+    const LaunchShape s = shape_420(p.upr, p.nrp, a.nframes, 8);
+    switch (a.dstfmt) {
+    case IMG_YUV422P: k_yuv420_rgb_yuv<D422><<<s.grid, s.block, 0, a.stream>>>(p); break;
+    case IMG_YUV420P: k_yuv420_rgb_yuv<D420><<<s.grid, s.block, 0, a.stream>>>(p); break;
+    default:          k_yuv420_rgb_yuv<D444><<<s.grid, s.block, 0, a.stream>>>(p); break;
+    }
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_yuv420_rgb_yuv");
+    return true;
 }
 
 bool convert_tma(const ConvertArgs &a)
