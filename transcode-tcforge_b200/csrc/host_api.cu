@@ -83,6 +83,16 @@ int pipe_slots()
     return n;
 }
 
+size_t pipe_chunk_bytes()
+{
+    static const size_t n = [] {
+        const char *e = getenv("ACGPU_PIPE_CHUNK_MB");
+        const int v = e ? atoi(e) : 16;
+        return (size_t)(v < 1 ? 1 : v > 256 ? 256 : v) << 20;
+    }();
+    return n;
+}
+
 DevCtx *ctx()
 {
     if (!bind_device()) return nullptr;
@@ -982,7 +992,7 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
     const bool preload = !overwrites_whole_dest(sf, df, width, height);
     // ~16 MiB of the larger side per chunk: big enough to amortise launches and reach full PCIe rate (tools/pcie_probe.py:
     // 16 MB copies already run at 56 GB/s), small enough that the fill/drain bubbles of the pipeline stay short
-    size_t per = (size_t)(16u << 20) / (sp > dp ? sp : dp);
+    size_t per = pipe_chunk_bytes() / (sp > dp ? sp : dp);
     if (per < 1) per = 1;
     if (per > (size_t)nframes) per = nframes;
     const size_t slot_bytes = per * (sp + dp);

@@ -577,7 +577,7 @@ int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int widt
         break;
     }
     const size_t big = ip > tp ? ip : tp;
-    size_t per = (size_t)(16u << 20) / big;
+    size_t per = pipe_chunk_bytes() / big;
     if (per < 1) per = 1;
     if (per > (size_t)nframes) per = (size_t)nframes;
     const size_t slot_bytes = per * (ip + (preload ? 3 : 2) * tp);
