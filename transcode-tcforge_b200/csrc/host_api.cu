@@ -77,7 +77,7 @@ int pipe_slots()
 {
     static const int n = [] {
         const char *e = getenv("ACGPU_PIPE_SLOTS");
-        const int v = e ? atoi(e) : 3;
+        const int v = e ? atoi(e) : 4;
         return v < 2 ? 2 : v > kPipeSlots ? kPipeSlots : v;
     }();
     return n;
@@ -87,7 +87,7 @@ size_t pipe_chunk_bytes()
 {
     static const size_t n = [] {
         const char *e = getenv("ACGPU_PIPE_CHUNK_MB");
-        const int v = e ? atoi(e) : 16;
+        const int v = e ? atoi(e) : 32;
         return (size_t)(v < 1 ? 1 : v > 256 ? 256 : v) << 20;
     }();
     return n;
@@ -990,8 +990,8 @@ int acgpu_imgconvert_frames_host(const uint8_t *src_frames, ImageFormat srcfmt, 
     const size_t sfb = frame_bytes(sf, width, height), dfb = frame_bytes(df, width, height);
     const size_t sp = align_up(sfb, 256), dp = align_up(dfb, 256);     // device frame pitches
     const bool preload = !overwrites_whole_dest(sf, df, width, height);
-    // ~16 MiB of the larger side per chunk: big enough to amortise launches and reach full PCIe rate (tools/pcie_probe.py:
-    // 16 MB copies already run at 56 GB/s), small enough that the fill/drain bubbles of the pipeline stay short
+    // ~32 MiB of the larger side per chunk in four slots: big enough to amortise launches and reach full PCIe rate, small
+    // enough that the fill / drain bubbles of the pipeline stay short (profiles/r2_experiments.md section 6: slots x chunk)
     size_t per = pipe_chunk_bytes() / (sp > dp ? sp : dp);
     if (per < 1) per = 1;
     if (per > (size_t)nframes) per = nframes;

@@ -13,8 +13,8 @@ namespace acgpu {
 
 constexpr int kMaxDev = 16;
 constexpr int kPipeSlots = 6;          // buffers of the host-frame pipelines; pipe_slots() of them are used
-int pipe_slots();                      // $ACGPU_PIPE_SLOTS, default 3
-size_t pipe_chunk_bytes();             // $ACGPU_PIPE_CHUNK_MB, default 16: bytes of the larger side per pipeline chunk
+int pipe_slots();                      // $ACGPU_PIPE_SLOTS, default 4
+size_t pipe_chunk_bytes();             // $ACGPU_PIPE_CHUNK_MB, default 32: bytes of the larger side per pipeline chunk
 
 struct Blob {               // small device-resident tables cached by content (row-op lists, weights)
     uint64_t hash;
