@@ -457,6 +457,7 @@ int run_on_devices(const char *who, int ndevices, int nframes, const std::functi
     int grain = nframes / (ndevices * 6);
     if (grain < 16) grain = 16;
     if (grain > (nframes + ndevices - 1) / ndevices) grain = (nframes + ndevices - 1) / ndevices;
+    if (ndevices == 1) grain = nframes;        // nothing to balance: one pipelined call
     std::lock_guard<std::mutex> call(g_multi_mutex);
     std::vector<int> ok((size_t)ndevices, 0);
     std::vector<std::string> why((size_t)ndevices);
