@@ -15,7 +15,8 @@ pass of the hot path over one batch of synthetic frames: ONE acgpu_imgconvert_ba
   cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host cores, bounded sample
   extra     the other BASELINE configs, each with the same keys (device-resident value, roofline, e2e and -- at N=1 -- the
             reference on the host cores): config 4 as ONE resident chain (3840x2160 YUV420P -> RGB24 -> YUV422P, one
-            stream per GPU: acgpu_chain_*), config 5 (1280x720 YUY2 -> YUV420P, batches of 64), config 3's row shapes
+            stream per GPU: acgpu_chain_*), config 5 (1280x720 YUY2 -> YUV420P, batches of 64), config 3's row shapes, and a
+            do_process_frame-shaped chain (-I 5 -B 45,80 -G 0.8: 1080p YUV420P -> deinterlaced, gamma-corrected 720p)
 Multi-GPU (--gpus N under torchrun): frames are sharded, each rank converts its own batch on its own GPU,
 no collective on the data path (frames are independent); weak scaling; time = max over ranks.
 `--impl reference` times the reference's own CPU path (aclib, stock ac_init(AC_ALL) => SSE2) on the host, and carries the
@@ -59,7 +60,7 @@ WORKLOADS = {
 METRIC = {
     "yuv420p_rgb24_1080p": "1080p frames/s (ac_imgconvert YUV420P->RGB24)",
 }
-EXTRA_DEFAULT = ["uhd_roundtrip", "yuy2_yuv420p_720p", "deinterlace_blend_1080p_rgb", "resize_1080_720_y"]
+EXTRA_DEFAULT = ["uhd_roundtrip", "yuy2_yuv420p_720p", "deinterlace_blend_1080p_rgb", "resize_1080_720_y", "process_frame_1080p"]
 
 
 def cpu_model() -> str:
