@@ -348,7 +348,16 @@ bool run_chain(DevCtx *c, acgpu_stream_t as, const Plan &pl, const acgpu_chain_o
             a.dst.p[0] = to2.p; a.dst.p[1] = to2.p + (size_t)g2.w * g2.h; a.dst.p[2] = a.dst.p[1] + chroma_plane_bytes(g2.fmt, g2.w, g2.h);
             a.dst.pitch = to2.pitch;
             tls.err[0] = 0;
-            if (convert_fused_yuv420_rgb_yuv(a)) {
+            // grid.y carries the frame index: longer sub-batches are cut into launches of 32768 frames, like every batch call
+            bool fused = true;
+            for (int f0 = 0; f0 < nf && fused; f0 += 32768) {
+                ConvertArgs b = a;
+                b.nframes = nf - f0 < 32768 ? nf - f0 : 32768;
+                for (int pl_ = 0; pl_ < 3; pl_++) { b.src.p[pl_] += (size_t)f0 * a.src.pitch; b.dst.p[pl_] += (size_t)f0 * a.dst.pitch; }
+                fused = convert_fused_yuv420_rgb_yuv(b);
+                if (!fused && f0 > 0) return false;       // cannot happen (same geometry as the first part); never mix the two forms
+            }
+            if (fused) {
                 tls.last_tier = 2;
                 outs_left -= 2;
                 cur = to2;

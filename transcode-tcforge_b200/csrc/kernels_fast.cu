@@ -946,10 +946,12 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 // [frames][rows][row_bytes / elem] tensor of `elem`-byte unsigned elements, box {box_x, box_y, 1}
+static thread_local bool t_encode_failed = false;     // the last tier-3 launch attempt stopped at a tensor-map encode (nothing was launched)
 static bool make_map3(CUtensorMap *m, const void *base, int elem, uint64_t row_bytes, uint64_t rows, uint64_t frames, uint64_t pitch,
                       uint32_t box_x, uint32_t box_y)
 {
     EncodeTiledFn enc = encode_tiled_fn();
+    t_encode_failed = true;
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return false; }
     const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
     const cuuint64_t dims[3] = {row_bytes / (uint64_t)elem, rows, frames}, strides[2] = {row_bytes, frames > 1 ? pitch : row_bytes * rows};
@@ -957,6 +959,7 @@ static bool make_map3(CUtensorMap *m, const void *base, int elem, uint64_t row_b
     const CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+    t_encode_failed = false;
     return true;
 }
 
@@ -1270,23 +1273,25 @@ bool convert_tma_auto(const ConvertArgs &a)
     const int upr = a.w / 16, lanes_row = ((upr + 31) / 32) * 32;
     if (upr * 10 < lanes_row * 8 || upr > 256 * 65535) return false;
     if (!encode_tiled_fn()) return false;
-    if (a.srcfmt == IMG_YUV420P) return (enabled & 1) && tma_loads_dst(a.dstfmt, p, a.nframes, a.stream);
+    // a geometry the tensor-map encoder refuses is not an error of the call: nothing was launched, tier 2 takes it
+    auto soft = [](bool launched) {
+        if (!launched && t_encode_failed) { t_encode_failed = false; set_error("%s", ""); }
+        return launched;
+    };
+    if (a.srcfmt == IMG_YUV420P) return (enabled & 1) && soft(tma_loads_dst(a.dstfmt, p, a.nframes, a.stream));
     const bool wins = a.srcfmt == IMG_YUV411P || (a.srcfmt == IMG_YUV422P && a.w >= 1920);
     if (!(enabled & (wins ? 2 : 4))) return false;
     switch (a.srcfmt) {
-    case IMG_YUV422P: return tma_rows_dst<S422>(a.dstfmt, p, a.nframes, a.stream);
-    case IMG_YUV444P: return tma_rows_dst<S444>(a.dstfmt, p, a.nframes, a.stream);
-    case IMG_YUV411P: return tma_rows_dst<S411>(a.dstfmt, p, a.nframes, a.stream);
-    case IMG_YUY2:    return tma_rows_dst<SYUY2>(a.dstfmt, p, a.nframes, a.stream);
-    case IMG_UYVY:    return tma_rows_dst<SUYVY>(a.dstfmt, p, a.nframes, a.stream);
-    case IMG_YVYU:    return tma_rows_dst<SYVYU>(a.dstfmt, p, a.nframes, a.stream);
+    case IMG_YUV422P: return soft(tma_rows_dst<S422>(a.dstfmt, p, a.nframes, a.stream));
+    case IMG_YUV444P: return soft(tma_rows_dst<S444>(a.dstfmt, p, a.nframes, a.stream));
+    case IMG_YUV411P: return soft(tma_rows_dst<S411>(a.dstfmt, p, a.nframes, a.stream));
+    case IMG_YUY2:    return soft(tma_rows_dst<SYUY2>(a.dstfmt, p, a.nframes, a.stream));
+    case IMG_UYVY:    return soft(tma_rows_dst<SUYVY>(a.dstfmt, p, a.nframes, a.stream));
+    case IMG_YVYU:    return soft(tma_rows_dst<SYVYU>(a.dstfmt, p, a.nframes, a.stream));
     default: return false;
     }
 }
 
-// YUV420P -> (any RGB layout) -> YUV420P / YUV422P / YUV444P in one pass.  `a` describes the OUTER pair: a.src is the
-// YUV420P batch, a.dst the final YUV batch.  Returns false without launching when outside the fused kernel's domain
-// (the chain then runs the two conversions).
 bool convert_fused_yuv420_rgb_yuv(const ConvertArgs &a)
 {
     if (a.srcfmt != IMG_YUV420P || (a.dstfmt != IMG_YUV422P && a.dstfmt != IMG_YUV420P && a.dstfmt != IMG_YUV444P)) return false;
