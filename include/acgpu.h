@@ -246,6 +246,16 @@ int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int widt
                             const acgpu_chain_op *ops, int nops, int nframes);
 int acgpu_chain_frames_host_multi(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
                                   const acgpu_chain_op *ops, int nops, int nframes, int ndevices);
+/* The same for frames that each live in a buffer of their own -- transcode's frame ring: one tc_bufalloc'd video_buf per
+ * vframe_list_t (tccore/frame.h:215-253, libtc/tcframes.c:214-229) -- or at any stride inside a larger buffer (a YUV4MPEG2
+ * stream under construction: "FRAME\n" + planes, encode/encode_yuv4mpeg.c:256-289).  src_frames[i] / dest_frames[i] point
+ * at frame i (YUV_INIT_PLANES layout); dest_frames[i] == src_frames[i] processes frame i in place as do_process_frame does
+ * (the frame is uploaded before its result comes back), any other overlap between the two lists is the caller's to avoid.
+ * One copy per frame and direction instead of one per chunk; everything else is the pipeline of acgpu_chain_frames_host. */
+int acgpu_chain_frame_list_host(const uint8_t *const *src_frames, ImageFormat fmt, int width, int height,
+                                uint8_t *const *dest_frames, const acgpu_chain_op *ops, int nops, int nframes);
+int acgpu_chain_frame_list_host_multi(const uint8_t *const *src_frames, ImageFormat fmt, int width, int height,
+                                      uint8_t *const *dest_frames, const acgpu_chain_op *ops, int nops, int nframes, int ndevices);
 
 /* Optional: stops the per-device host threads of the *_multi calls while the CUDA runtime is still alive.  Without it
  * they are abandoned at process exit (never joined from a static destructor). */

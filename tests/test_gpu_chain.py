@@ -252,6 +252,108 @@ def test_chain_fuzz(ac, tcv, conv):
     assert done >= 40
 
 
+# ---- frame lists: every frame in a buffer of its own (transcode's frame ring), in place, or inside a stream buffer -----
+def ptr_list(addrs):
+    return (C.c_void_p * len(addrs))(*addrs)
+
+
+def run_list(ac, src_bufs, dst_bufs, fmt, w, h, stages, multi=False):
+    ops = pkg.chain_ops(stages)
+    sp, dp = ptr_list([b.ctypes.data for b in src_bufs]), ptr_list([b.ctypes.data for b in dst_bufs])
+    if multi:
+        return ac.lib.acgpu_chain_frame_list_host_multi(sp, fmt, w, h, dp, ops, len(stages), len(src_bufs), 0)
+    return ac.lib.acgpu_chain_frame_list_host(sp, fmt, w, h, dp, ops, len(stages), len(src_bufs))
+
+
+@pytest.mark.parametrize("multi", [False, True], ids=["one_device", "all_devices"])
+def test_frame_list_scattered_buffers(ac, tcv, conv, multi):
+    # 11 frames, each in its own (pageable) allocation with its own guard band, given in shuffled address order
+    w, h, nf = 640, 480, 11
+    stages = [(DEINTERLACE, 5), (CONVERT, F.IMG_RGB24), (FLIP_H,), (CONVERT, F.IMG_YUV422P)]
+    frames = frames_of(F.IMG_YUV420P, w, h, nf, 900)
+    want, geo = expect(tcv, conv, frames, F.IMG_YUV420P, w, h, stages)
+    inb, outb = F.frame_bytes(F.IMG_YUV420P, w, h), F.frame_bytes(geo[0], geo[1], geo[2])
+    order = np.random.default_rng(5).permutation(nf)
+    src_bufs = [None] * nf
+    dst_bufs = [None] * nf
+    for i in order:          # allocation order != list order
+        src_bufs[i] = np.concatenate([frames[i], np.full(32, 0xEE, np.uint8)])
+        dst_bufs[i] = np.full(outb + 48, 0x55, np.uint8)
+    assert run_list(ac, src_bufs, dst_bufs, F.IMG_YUV420P, w, h, stages, multi) == 1, ac.last_error()
+    for i in range(nf):
+        assert np.array_equal(dst_bufs[i][:outb], want[i]), i
+        assert (dst_bufs[i][outb:] == 0x55).all(), "wrote past frame %d" % i
+        assert np.array_equal(src_bufs[i][:inb], frames[i]) and (src_bufs[i][inb:] == 0xEE).all(), "source %d modified" % i
+
+
+def test_frame_list_in_place_like_do_process_frame(ac, tcv, conv):
+    # dest_frames[i] == src_frames[i]: the frame buffer is processed in place (video_trans.c works on video_buf itself);
+    # the chain shrinks the frame, bytes behind the new frame keep the old picture
+    w, h, nf = 720, 576, 5
+    stages = [(CLIP, 8, 8, 16, 16), (DEINTERLACE, 1), (RESIZE, -6, -4), (GAMMA, 0.8)]
+    frames = frames_of(F.IMG_YUV420P, w, h, nf, 910)
+    want, geo = expect(tcv, conv, frames, F.IMG_YUV420P, w, h, stages)
+    outb = F.frame_bytes(geo[0], geo[1], geo[2])
+    bufs = [ac.pinned(frames.shape[1]) for _ in range(nf)]
+    for i in range(nf):
+        bufs[i].array[:] = frames[i]
+    ops = pkg.chain_ops(stages)
+    pl = ptr_list([b.ptr for b in bufs])
+    assert ac.lib.acgpu_chain_frame_list_host(pl, F.IMG_YUV420P, w, h, pl, ops, len(stages), nf) == 1, ac.last_error()
+    for i in range(nf):
+        got = np.asarray(bufs[i].array)
+        assert np.array_equal(got[:outb], want[i]), i
+        assert np.array_equal(got[outb:], frames[i][outb:]), "bytes behind the new frame %d changed" % i
+        bufs[i].free()
+
+
+def test_frame_list_into_a_yuv4mpeg_stream_buffer(ac, tcv, conv):
+    # encode_yuv4mpeg.c:256-289: tcv_convert to YUV420P, then "FRAME\n" + the planes go to the stream.  Here the frames of a
+    # chain land behind their headers directly: dest_frames[i] = stream + header + i * (6 + frame bytes)
+    w, h, nf = 352, 288, 9
+    stages = [(CONVERT, F.IMG_YUV420P)]
+    frames = frames_of(F.IMG_RGB24, w, h, nf, 920)
+    want, geo = expect(tcv, conv, frames, F.IMG_RGB24, w, h, stages)
+    outb = F.frame_bytes(F.IMG_YUV420P, w, h)
+    head = b"YUV4MPEG2 W352 H288 F25:1 Ip A1:1 C420jpeg\n"
+    stream = ac.pinned(len(head) + nf * (6 + outb))
+    st = stream.array
+    st[:] = 0x55
+    st[:len(head)] = np.frombuffer(head, np.uint8)
+    for i in range(nf):
+        o = len(head) + i * (6 + outb)
+        st[o:o + 6] = np.frombuffer(b"FRAME\n", np.uint8)
+    src = ac.pinned(frames.size)
+    src.array[:] = frames.reshape(-1)
+    sp = ptr_list([src.ptr + i * frames.shape[1] for i in range(nf)])
+    dp = ptr_list([stream.ptr + len(head) + i * (6 + outb) + 6 for i in range(nf)])
+    ops = pkg.chain_ops(stages)
+    assert ac.lib.acgpu_chain_frame_list_host(sp, F.IMG_RGB24, w, h, dp, ops, 1, nf) == 1, ac.last_error()
+    expect_stream = bytearray(head)
+    for i in range(nf):
+        expect_stream += b"FRAME\n" + want[i].tobytes()
+    assert bytes(np.asarray(st)) == bytes(expect_stream)
+    src.free(); stream.free()
+
+
+def test_frame_list_keeps_alpha_and_rejects_null_frames(ac, tcv, conv):
+    w, h, nf = 128, 32, 3
+    stages = [(CONVERT, F.IMG_ARGB32)]
+    frames = frames_of(F.IMG_YUY2, w, h, nf, 930)
+    want, _ = expect(tcv, conv, frames, F.IMG_YUY2, w, h, stages)       # the checker's destination prefill is 0x55
+    src_bufs = [frames[i].copy() for i in range(nf)]
+    dst_bufs = [np.full(w * h * 4, 0x55, np.uint8) for _ in range(nf)]
+    assert run_list(ac, src_bufs, dst_bufs, F.IMG_YUY2, w, h, stages) == 1, ac.last_error()
+    for i in range(nf):
+        assert np.array_equal(dst_bufs[i], want[i]), i
+    ops = pkg.chain_ops(stages)
+    sp = ptr_list([src_bufs[0].ctypes.data, None, src_bufs[2].ctypes.data])
+    dp = ptr_list([b.ctypes.data for b in dst_bufs])
+    assert ac.lib.acgpu_chain_frame_list_host(sp, F.IMG_YUY2, w, h, dp, ops, 1, nf) == 0 and "frame 1" in ac.last_error()
+    assert ac.lib.acgpu_chain_frame_list_host(None, F.IMG_YUY2, w, h, dp, ops, 1, nf) == 0
+    assert ac.lib.acgpu_chain_frame_list_host(None, F.IMG_YUY2, w, h, None, ops, 1, 0) == 1     # nothing to do
+
+
 def test_chain_rejections(ac):
     w, h = 64, 32
     bad = [

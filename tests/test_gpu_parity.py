@@ -134,11 +134,12 @@ def test_config2_matrix_1080p(ac, chk, a, b):
 
 # ---- every pair at full size: the grid-stride paths (block clamp, several trips per block, frame segments) that the
 # small all-pairs tests never reach (testsuite/test-imgconvert.c runs its matrix at one size only, 768x512) -------------
-@pytest.mark.parametrize("size", [(1920, 1080), (1280, 720)], ids=lambda s: f"{s[0]}x{s[1]}")
+# PAL is BASELINE config 1's size (4:2:0 chroma rows of 360 bytes: not 16-byte aligned), UHD config 4's.
+@pytest.mark.parametrize("size", [(1920, 1080), (1280, 720), (720, 576), (3840, 2160)], ids=lambda s: f"{s[0]}x{s[1]}")
 @pytest.mark.parametrize("srcfmt", F.FORMATS_16, ids=lambda f: F.NAMES[f])
 def test_all_pairs_full_size(ac, chk, srcfmt, size):
     w, h = size
-    nf = 2
+    nf = 1 if w * h > 4_000_000 else 2
     frames = np.stack([ck.random_frame(srcfmt, w, h, seed=70 + i) for i in range(nf)])
     for dstfmt in F.FORMATS_16:
         dfb = F.frame_bytes(dstfmt, w, h)

@@ -86,6 +86,7 @@ ABI_SYMBOLS = [
     "acgpu_clip_batch", "acgpu_reduce_batch", "acgpu_flip_v_batch", "acgpu_flip_h_batch",
     "acgpu_gamma_correct_batch", "acgpu_antialias_batch",
     "acgpu_chain_output", "acgpu_chain_batch", "acgpu_chain_frames_host", "acgpu_chain_frames_host_multi", "acgpu_shutdown",
+    "acgpu_chain_frame_list_host", "acgpu_chain_frame_list_host_multi",
     "acgpu_bufalloc", "acgpu_buffree", "acgpu_host_register", "acgpu_host_unregister", "acgpu_pointer_kind",
 ]
 
@@ -133,6 +134,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "acgpu_chain_batch": (i32, [vp, i32, i32, i32, sz, vp, sz, C.POINTER(ChainOp), i32, i32, vp]),
         "acgpu_chain_frames_host": (i32, [vp, i32, i32, i32, vp, C.POINTER(ChainOp), i32, i32]),
         "acgpu_chain_frames_host_multi": (i32, [vp, i32, i32, i32, vp, C.POINTER(ChainOp), i32, i32, i32]),
+        "acgpu_chain_frame_list_host": (i32, [C.POINTER(vp), i32, i32, i32, C.POINTER(vp), C.POINTER(ChainOp), i32, i32]),
+        "acgpu_chain_frame_list_host_multi": (i32, [C.POINTER(vp), i32, i32, i32, C.POINTER(vp), C.POINTER(ChainOp), i32, i32, i32]),
         "acgpu_shutdown": (None, []),
         "acgpu_bufalloc": (vp, [sz]), "acgpu_buffree": (None, [vp]), "acgpu_host_register": (i32, [vp, sz]),
         "acgpu_host_unregister": (i32, [vp]), "acgpu_pointer_kind": (i32, [vp]),

@@ -107,6 +107,7 @@ struct TcvWindow {
     uint32_t cl, cn, sxb;
     uint32_t fill;                // fill byte replicated into all four bytes
     int      vec;                 // set by the launcher: destination chunks are 16-byte aligned
+    uint32_t div_m, div_s;        // set by the launcher: off / dBpl as a multiply-high (tcvops.cu window_row_of)
 };
 bool tcv_window_launch(TcvWindow p, int nframes, cudaStream_t st);
 bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int ow, int oh, int rw, int rh,

@@ -561,17 +561,16 @@ int acgpu_chain_batch(const uint8_t *src, ImageFormat fmt, int width, int height
     return needs_scratch ? (arena_release(c, st) ? 1 : 0) : 1;
 }
 
-// Host frames: tightly packed runs in `src_frames` / `dest_frames` (best: acgpu_host_alloc memory).  Three pipeline slots,
-// each with its own stream: upload chunk k+1 and download chunk k-1 while chunk k is processed.
-int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
-                            const acgpu_chain_op *ops, int nops, int nframes)
+// The pipeline behind the host-frame chain calls.  Frame i of the run lies at src_at(i) / dst_at(i) in host memory (best:
+// acgpu_host_alloc / acgpu_bufalloc memory).  A few pipeline slots, each with its own stream: upload chunk k+1 and download
+// chunk k-1 while chunk k is processed.  `contiguous`: the frames are one tightly packed run, so a chunk travels as one
+// strided copy; otherwise every frame is a copy of its own (transcode's frame ring: one tc_bufalloc'd buffer per
+// vframe_list_t, tccore/frame.h:215-253).
+extern "C++" {
+template <class SrcAt, class DstAt>
+static int chain_pipeline(const char *who, DevCtx *c, const Plan &pl, const acgpu_chain_op *ops, int nops, int nframes,
+                          bool contiguous, SrcAt src_at, DstAt dst_at)
 {
-    DevCtx *c = ctx();
-    if (!c) return 0;
-    if (!src_frames || !dest_frames) { set_error("acgpu_chain_frames_host: null frame pointer"); return 0; }
-    Plan pl;
-    if (!make_plan(fmt, width, height, ops, nops, &pl)) return 0;
-    if (nframes <= 0) return 1;
     const size_t inb = geo_bytes(pl.geo.front()), outb = geo_bytes(pl.geo.back());
     const size_t ip = align_up(inb, 256), tp = align_up(pl.max_bytes + 256, 256);
     // The last conversion may leave destination bytes alone (alpha of YUV -> 32-bit RGB): the caller's destination frames
@@ -599,6 +598,21 @@ int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int widt
             c->pipe_cap[s] = slot_bytes;
         }
     }
+    // host run <-> device rows of `dev_pitch` bytes, frames f0 .. f0+n-1
+    auto copy_frames = [&](uint8_t *dev, size_t dev_pitch, int f0, int n, size_t bytes, bool to_device, bool from_dst, cudaStream_t st) {
+        if (contiguous) {
+            uint8_t *host = from_dst ? dst_at(f0) : const_cast<uint8_t *>(src_at(f0));
+            return to_device ? check(cudaMemcpy2DAsync(dev, dev_pitch, host, bytes, bytes, (size_t)n, cudaMemcpyHostToDevice, st), "H2D frames")
+                             : check(cudaMemcpy2DAsync(host, bytes, dev, dev_pitch, bytes, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H frames");
+        }
+        for (int i = 0; i < n; i++) {
+            uint8_t *host = from_dst ? dst_at(f0 + i) : const_cast<uint8_t *>(src_at(f0 + i));
+            const bool ok = to_device ? check(cudaMemcpyAsync(dev + (size_t)i * dev_pitch, host, bytes, cudaMemcpyHostToDevice, st), "H2D frame")
+                                      : check(cudaMemcpyAsync(host, dev + (size_t)i * dev_pitch, bytes, cudaMemcpyDeviceToHost, st), "D2H frame");
+            if (!ok) return false;
+        }
+        return true;
+    };
     int chunk = 0;
     for (int f0 = 0; f0 < nframes; f0 += (int)per, chunk++) {
         const int s = chunk % pipe_slots();
@@ -606,18 +620,50 @@ int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int widt
         cudaStream_t st = c->pipe_stream[s];
         acgpu_stream_t as = reinterpret_cast<acgpu_stream_t>(st);
         Buf in{c->pipe_buf[s], ip}, s0{in.p + per * ip, tp}, s1{s0.p + per * tp, tp}, out{nullptr, 0};
-        if (!check(cudaMemcpy2DAsync(in.p, ip, src_frames + (size_t)f0 * inb, inb, inb, (size_t)n, cudaMemcpyHostToDevice, st), "H2D frames")) return 0;
+        if (!copy_frames(in.p, ip, f0, n, inb, true, false, st)) return 0;
         if (preload) {
             out = Buf{s1.p + per * tp, tp};
-            if (!check(cudaMemcpy2DAsync(out.p, tp, dest_frames + (size_t)f0 * outb, outb, outb, (size_t)n, cudaMemcpyHostToDevice, st), "H2D dest frames")) return 0;
+            if (!copy_frames(out.p, tp, f0, n, outb, true, true, st)) return 0;
         }
         Buf res;
         if (!run_chain(c, as, pl, ops, nops, in, true, s0, s1, out, n, &res)) return 0;
-        if (!check(cudaMemcpy2DAsync(dest_frames + (size_t)f0 * outb, outb, res.p, res.pitch, outb, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H frames")) return 0;
+        if (!copy_frames(res.p, res.pitch, f0, n, outb, false, true, st)) return 0;
     }
     for (int s = 0; s < pipe_slots(); s++)
-        if (!check(cudaStreamSynchronize(c->pipe_stream[s]), "acgpu_chain_frames_host")) return 0;
+        if (!check(cudaStreamSynchronize(c->pipe_stream[s]), who)) return 0;
     return 1;
+}
+}  // extern "C++"
+
+// Host frames: tightly packed runs in `src_frames` / `dest_frames`.
+int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
+                            const acgpu_chain_op *ops, int nops, int nframes)
+{
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    if (!src_frames || !dest_frames) { set_error("acgpu_chain_frames_host: null frame pointer"); return 0; }
+    Plan pl;
+    if (!make_plan(fmt, width, height, ops, nops, &pl)) return 0;
+    if (nframes <= 0) return 1;
+    const size_t inb = geo_bytes(pl.geo.front()), outb = geo_bytes(pl.geo.back());
+    return chain_pipeline("acgpu_chain_frames_host", c, pl, ops, nops, nframes, true,
+                          [=](int i) { return src_frames + (size_t)i * inb; }, [=](int i) { return dest_frames + (size_t)i * outb; });
+}
+
+// Host frames that each have a buffer of their own: src_frames[i] / dest_frames[i] point at frame i.
+int acgpu_chain_frame_list_host(const uint8_t *const *src_frames, ImageFormat fmt, int width, int height,
+                                uint8_t *const *dest_frames, const acgpu_chain_op *ops, int nops, int nframes)
+{
+    DevCtx *c = ctx();
+    if (!c) return 0;
+    Plan pl;
+    if (!make_plan(fmt, width, height, ops, nops, &pl)) return 0;
+    if (nframes <= 0) return 1;
+    if (!src_frames || !dest_frames) { set_error("acgpu_chain_frame_list_host: null frame list"); return 0; }
+    for (int i = 0; i < nframes; i++)
+        if (!src_frames[i] || !dest_frames[i]) { set_error("acgpu_chain_frame_list_host: frame %d is a null pointer", i); return 0; }
+    return chain_pipeline("acgpu_chain_frame_list_host", c, pl, ops, nops, nframes, false,
+                          [=](int i) { return src_frames[i]; }, [=](int i) { return dest_frames[i]; });
 }
 
 int acgpu_chain_frames_host_multi(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
@@ -628,6 +674,17 @@ int acgpu_chain_frames_host_multi(const uint8_t *src_frames, ImageFormat fmt, in
     const size_t inb = geo_bytes(pl.geo.front()), outb = geo_bytes(pl.geo.back());
     return run_on_devices("acgpu_chain_frames_host_multi", ndevices, nframes, [=](int, int f0, int f1) {
         return acgpu_chain_frames_host(src_frames + (size_t)f0 * inb, fmt, width, height, dest_frames + (size_t)f0 * outb, ops, nops, f1 - f0) == 1;
+    });
+}
+
+int acgpu_chain_frame_list_host_multi(const uint8_t *const *src_frames, ImageFormat fmt, int width, int height,
+                                      uint8_t *const *dest_frames, const acgpu_chain_op *ops, int nops, int nframes, int ndevices)
+{
+    Plan pl;
+    if (!make_plan(fmt, width, height, ops, nops, &pl)) return 0;
+    if (nframes > 0 && (!src_frames || !dest_frames)) { set_error("acgpu_chain_frame_list_host_multi: null frame list"); return 0; }
+    return run_on_devices("acgpu_chain_frame_list_host_multi", ndevices, nframes, [=](int, int f0, int f1) {
+        return acgpu_chain_frame_list_host(src_frames + f0, fmt, width, height, dest_frames + f0, ops, nops, f1 - f0) == 1;
     });
 }
 

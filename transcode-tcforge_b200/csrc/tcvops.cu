@@ -61,28 +61,64 @@ __device__ __forceinline__ uint32_t window_byte(const TcvWindow &p, const uint8_
     return src[(size_t)sr * p.sBpl + p.sxb + (xb - p.cl)];
 }
 
-// One destination chunk: classified, fetched (whole chunks only) and returned; the caller stores it.  `kind` tells the
-// caller what to do: 0 = nothing (past the end), 1 = store v, 2 = byte-granular tail / unaligned destination.
-__device__ __forceinline__ int window_chunk(const TcvWindow &p, const uint8_t *src, uint32_t c, uint32_t N, uint4 &v)
+// off / dBpl without a division instruction: the launcher supplies m = floor(2^(32+s) / dBpl) (capped at 2^32 - 1) with
+// s = floor(log2 dBpl); the estimate is at most one too small for every 32-bit off, one compare fixes it.
+__device__ __forceinline__ void window_row_of(const TcvWindow &p, uint32_t off, uint32_t &y, uint32_t &xb)
+{
+    y = __umulhi(off, p.div_m) >> p.div_s;
+    xb = off - y * p.dBpl;
+    if (xb >= p.dBpl) { y++; xb -= p.dBpl; }
+}
+
+// Bytes [sh, sh + 16) of the 32 bytes lo | hi, sh = 0..15, without a branch: drop two words, drop one word, shift by bytes.
+__device__ __forceinline__ uint4 shift16(const uint4 &lo, const uint4 &hi, uint32_t sh)
+{
+    const bool two = (sh & 8u) != 0, one = (sh & 4u) != 0;
+    const uint32_t x0 = two ? lo.z : lo.x, x1 = two ? lo.w : lo.y, x2 = two ? hi.x : lo.z, x3 = two ? hi.y : lo.w,
+                   x4 = two ? hi.z : hi.x, x5 = two ? hi.w : hi.y;
+    const uint32_t y0 = one ? x1 : x0, y1 = one ? x2 : x1, y2 = one ? x3 : x2, y3 = one ? x4 : x3, y4 = one ? x5 : x4;
+    const uint32_t bs = (sh & 3u) * 8u;
+    return make_uint4(__funnelshift_r(y0, y1, bs), __funnelshift_r(y1, y2, bs), __funnelshift_r(y2, y3, bs), __funnelshift_r(y3, y4, bs));
+}
+
+// One destination chunk: classified and its loads ISSUED; nothing here waits for them, so the chunks of a trip are all in
+// flight together (shifting inside this step made every unaligned chunk wait for its own data before the next one was
+// even requested).  kind: 0 = nothing (past the end, or a mixed chunk: those belong to the second phase), 1 = store lo
+// (an aligned source), 2 = byte-granular tail / unaligned destination, 3 = store shift16(lo, hi, sh), 4 = store the fill.
+// SHIFTED = false: the launcher has checked that every chunk's source is 16-byte aligned (whole-unit crops, borders,
+// rows-only reduce): one load per chunk and no shift state, which keeps that kernel at the copy rate.
+struct WinChunk { uint4 lo, hi; uint32_t sh; int kind; };
+template <bool SHIFTED>
+__device__ __forceinline__ void window_chunk(const TcvWindow &p, const uint8_t *src, uint32_t c, uint32_t N, WinChunk &o)
 {
     const uint32_t off = c * 16;
-    if (off >= N) return 0;
-    if (!(p.vec && off + 16 <= N)) return 2;
-    const uint32_t y = off / p.dBpl, xb = off - y * p.dBpl;
-    if (xb + 16 <= p.dBpl) {
-        const int sr = (int)y * p.row_mul + p.row_add;
-        const bool row_ok = sr >= 0 && sr < p.srows;
-        if (!row_ok || xb + 16 <= p.cl || xb >= p.cl + p.cn) {
-            v = make_uint4(p.fill, p.fill, p.fill, p.fill);
-            return 1;
-        }
-        if (xb >= p.cl && xb + 16 <= p.cl + p.cn) {
-            v = ld16_any<false>(src + (size_t)sr * p.sBpl + p.sxb + (xb - p.cl));
-            return 1;
-        }
+    o.kind = 0;
+    if (off >= N) return;
+    if (!(p.vec && off + 16 <= N)) { o.kind = 2; return; }
+    uint32_t y, xb;
+    window_row_of(p, off, y, xb);
+    if (xb + 16 > p.dBpl) return;
+    const int sr = (int)y * p.row_mul + p.row_add;
+    if (sr < 0 || sr >= p.srows || xb + 16 <= p.cl || xb >= p.cl + p.cn) { o.kind = 4; return; }
+    if (!(xb >= p.cl && xb + 16 <= p.cl + p.cn)) return;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src + (size_t)sr * p.sBpl + p.sxb + (xb - p.cl));
+    if (!SHIFTED) {
+        o.lo = __ldg(reinterpret_cast<const uint4 *>(a));
+        o.kind = 1;
+        return;
     }
-    // mixed chunk (border / row end inside it): walk its 16 bytes with a running (row, column)
-    uint32_t w[4] = {0, 0, 0, 0}, yy = y, xx = xb;
+    const uint4 *q = reinterpret_cast<const uint4 *>(a & ~(uintptr_t)15);
+    o.sh = (uint32_t)(a & 15);
+    o.lo = __ldg(q);
+    if (o.sh) o.hi = __ldg(q + 1);        // an unaligned chunk ends inside the next block; an aligned one may end the buffer
+    o.kind = o.sh ? 3 : 1;
+}
+
+// A chunk with a row end or a border edge inside it: its 16 bytes one by one with a running (row, column).
+__device__ __forceinline__ uint4 window_mixed_chunk(const TcvWindow &p, const uint8_t *src, uint32_t off)
+{
+    uint32_t w[4] = {0, 0, 0, 0}, yy, xx;
+    window_row_of(p, off, yy, xx);
     int sr = (int)yy * p.row_mul + p.row_add;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -91,12 +127,18 @@ __device__ __forceinline__ int window_chunk(const TcvWindow &p, const uint8_t *s
         w[i >> 2] |= b << (8 * (i & 3));
         if (++xx == p.dBpl) { xx = 0; yy++; sr += p.row_mul; }
     }
-    v = make_uint4(w[0], w[1], w[2], w[3]);
-    return 1;
+    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 constexpr int kWinUnroll = 4;     // independent 16-byte loads in flight per thread (a lone load per thread is latency-bound)
 
+// Two phases.  (1) every whole chunk that lies in ONE region (copy span, border, filled row): one load, one store, four
+// chunks in flight per thread.  (2) the mixed chunks, found from the other side: a chunk is mixed exactly when a row
+// start, the left edge of the copy span or its right edge falls strictly inside it, so the (at most three per row)
+// edges are enumerated and each rebuilds the chunk it cuts byte by byte.  Leaving them in phase 1 made every warp run
+// the byte path (a 1912-byte row puts one mixed chunk into every 120: 0.55 of the copy rate); two edges in one chunk
+// write the same sixteen bytes twice.
+template <bool SHIFTED>
 __global__ void __launch_bounds__(kThreads) k_window(TcvWindow p)
 {
     const uint8_t *src = p.src + (size_t)blockIdx.y * p.spitch;
@@ -104,19 +146,32 @@ __global__ void __launch_bounds__(kThreads) k_window(TcvWindow p)
     const uint32_t N = p.dBpl * (uint32_t)p.drows, nchunks = (N + 15) / 16;
     const uint32_t per_block = kThreads * kWinUnroll;
     for (uint32_t base = blockIdx.x * per_block; base < nchunks; base += gridDim.x * per_block) {
-        uint4 v[kWinUnroll];
-        int kind[kWinUnroll];
+        WinChunk ch[kWinUnroll];
 #pragma unroll
-        for (int k = 0; k < kWinUnroll; k++) kind[k] = window_chunk(p, src, base + k * kThreads + threadIdx.x, N, v[k]);
+        for (int k = 0; k < kWinUnroll; k++) window_chunk<SHIFTED>(p, src, base + k * kThreads + threadIdx.x, N, ch[k]);
 #pragma unroll
         for (int k = 0; k < kWinUnroll; k++) {
             const uint32_t off = (base + k * kThreads + threadIdx.x) * 16;
-            if (kind[k] == 1) {
-                stg128(dst + off, v[k]);
-            } else if (kind[k] == 2) {
+            if (ch[k].kind == 1) {
+                stg128(dst + off, ch[k].lo);
+            } else if (SHIFTED && ch[k].kind == 3) {
+                stg128(dst + off, shift16(ch[k].lo, ch[k].hi, ch[k].sh));
+            } else if (ch[k].kind == 4) {
+                stg128(dst + off, make_uint4(p.fill, p.fill, p.fill, p.fill));
+            } else if (ch[k].kind == 2) {
                 for (uint32_t i = 0; i < 16 && off + i < N; i++) dst[off + i] = (uint8_t)window_byte(p, src, off + i);
             }
         }
+    }
+    if (!p.vec) return;
+    const uint32_t nedges = 3u * (uint32_t)p.drows;
+    for (uint32_t e = blockIdx.x * kThreads + threadIdx.x; e < nedges; e += gridDim.x * kThreads) {
+        const uint32_t y = e / 3u, k = e - 3u * y;
+        if ((k == 1 && p.cl == 0) || (k == 2 && p.cl + p.cn >= p.dBpl)) continue;      // the same place as a row start
+        const uint32_t b = y * p.dBpl + (k == 0 ? 0u : k == 1 ? p.cl : p.cl + p.cn);
+        const uint32_t off = b & ~15u;
+        if (off == b || off + 16 > N) continue;                                         // on a chunk boundary / the byte-granular tail
+        stg128(dst + off, window_mixed_chunk(p, src, off));
     }
 }
 
@@ -354,7 +409,12 @@ __global__ void __launch_bounds__(kThreads) k_flip_h(const uint8_t *src0, size_t
 
 // ---------------------------------------------------------------------------------------------------
 // tcv_gamma_correct (tcvideo.c:840-858): dest[i] = table[src[i]].  The 256-byte table (built on the host with the
-// reference's double arithmetic) sits in shared memory as 64 words: byte lookups conflict at most two-way.
+// reference's double arithmetic) sits in shared memory as 64 words: byte lookups conflict at most two-way.  (32 private
+// copies of 32-bit entries, conflict-free by construction, were measured and lost: 0.91 -> 0.81-0.84 of the copy rate --
+// the fill of 32 KB per block and the third instruction per lookup cost more than the replays, profiles/r2_experiments.md.)
+#ifndef ACGPU_LUT_UNROLL
+#define ACGPU_LUT_UNROLL 2
+#endif
 __global__ void __launch_bounds__(kThreads) k_lut(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
                                                    const uint8_t *table, uint32_t nbytes, int vec)
 {
@@ -374,18 +434,25 @@ __global__ void __launch_bounds__(kThreads) k_lut(const uint8_t *src0, size_t sp
         }
         return make_uint4(out[0], out[1], out[2], out[3]);
     };
-    // two chunks per trip: both loads are issued before either is used (one 16-byte load per thread in flight does not
+    // several chunks per trip: all loads are issued before any is used (one 16-byte load per thread in flight does not
     // cover HBM latency)
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += 2 * stride) {
-        const uint32_t off0 = c * 16, c1 = c + stride, off1 = c1 * 16;
-        const bool whole0 = vec && off0 + 16 <= nbytes, has1 = c1 < nchunks, whole1 = has1 && vec && off1 + 16 <= nbytes;
-        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-        if (whole0) v0 = *reinterpret_cast<const uint4 *>(src + off0);
-        if (whole1) v1 = *reinterpret_cast<const uint4 *>(src + off1);
-        if (whole0) stg128(dst + off0, map16(v0));
-        else for (uint32_t i = off0; i < off0 + 16 && i < nbytes; i++) dst[i] = s_t[src[i]];
-        if (whole1) stg128(dst + off1, map16(v1));
-        else if (has1) for (uint32_t i = off1; i < off1 + 16 && i < nbytes; i++) dst[i] = s_t[src[i]];
+    constexpr int U = ACGPU_LUT_UNROLL;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += U * stride) {
+        uint4 v[U];
+        bool whole[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const uint32_t ck = c + k * stride, off = ck * 16;
+            whole[k] = ck < nchunks && vec && off + 16 <= nbytes;
+            v[k] = make_uint4(0, 0, 0, 0);
+            if (whole[k]) v[k] = *reinterpret_cast<const uint4 *>(src + off);
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const uint32_t ck = c + k * stride, off = ck * 16;
+            if (whole[k]) stg128(dst + off, map16(v[k]));
+            else if (ck < nchunks) for (uint32_t i = off; i < off + 16 && i < nbytes; i++) dst[i] = s_t[src[i]];
+        }
     }
 }
 
@@ -621,7 +688,17 @@ bool tcv_window_launch(TcvWindow p, int nframes, cudaStream_t st)
     p.vec = al16p(p.dst, p.dpitch, nframes) ? 1 : 0;
     const uint64_t N = (uint64_t)p.dBpl * p.drows;
     if (N == 0) return true;
-    k_window<<<grid_for((N + 15) / 16 / kWinUnroll + 1, nframes), kThreads, 0, st>>>(p);
+    uint32_t s = 0;
+    while ((2u << s) <= p.dBpl && s < 31) s++;
+    const uint64_t m = ((uint64_t)1 << (32 + s)) / p.dBpl;
+    p.div_s = s; p.div_m = m > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)m;
+    // every whole chunk's source 16-byte aligned?  (chunk at byte xb of destination row y reads source row
+    // y * row_mul + row_add from byte sxb + xb - cl on)
+    const bool aligned = p.vec && p.sBpl % 16 == 0 && p.dBpl % 16 == 0 && (nframes <= 1 || p.spitch % 16 == 0)
+                      && ((reinterpret_cast<uintptr_t>(p.src) + p.sxb - p.cl) & 15) == 0;
+    const dim3 g = grid_for((N + 15) / 16 / kWinUnroll + 1, nframes);
+    if (aligned) k_window<false><<<g, kThreads, 0, st>>>(p);
+    else k_window<true><<<g, kThreads, 0, st>>>(p);
     note_launch();
     ACGPU_CHECK_LAUNCH("k_window");
     return true;
