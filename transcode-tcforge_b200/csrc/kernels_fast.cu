@@ -1084,6 +1084,44 @@ bool fast_rgb2yuv(const ConvertArgs &a, const FastParams &p)
 // straight to the dp2a accumulators of k_rgb2yuv.  The intermediate's byte order does not matter -- the second conversion
 // reads the channels it was written with -- so every RGB layout fuses to the same code.  Bit-identical to the two calls;
 // 3.5 bytes of HBM traffic per pixel instead of 9.5.
+// Form of the arithmetic (ACGPU_FUSED_IMAD, compile time, default 0).  0: as the two kernels do it -- the channel bytes are
+// packed into one word per pixel (two PRMT) and every component is two dp2a on that word; with the yuv->rgb steps that is ~17
+// of 21 instructions per pixel on the ALU pipe (IDP, VIADDMNMX, PRMT), which runs at 65 % with the multiplier pipe at 35 %
+// (profiles/r2_ncu_summaries.md).  1: the channel comes out of the scale step as an integer -- one multiply-high with a 64-bit
+// addend gives floor((jc * 1220944 + 2^23) / 2^24) -- and every component is three multiply-adds on those integers: no packing,
+// no dp2a, 10 of 21 instructions per pixel on each pipe.  MEASURED AND REJECTED: bit-identical, but 128.8 k -> 106.9 k UHD
+// frames/s (0.57 -> 0.47 of the copy rate): the integer multiplier is the narrower pipe on this part, the balanced mix is the
+// slower one (profiles/r2_experiments.md section 3b).
+#ifndef ACGPU_FUSED_IMAD
+#define ACGPU_FUSED_IMAD 0
+#endif
+template <int BIAS>
+__device__ __forceinline__ uint32_t channel_int(uint32_t yword, uint32_t ysel, int c)
+{
+    const int j = (int)__dp4a(yword, ysel, (uint32_t)c);
+    const int jc = BIAS ? __viaddmin_s32_relu(j, -BIAS, pixmath::kJMax) : __vimin_s32_relu(j, pixmath::kJMax);
+    return (uint32_t)(((uint64_t)(uint32_t)jc * (uint64_t)(pixmath::kJMul * 256u) + ((uint64_t)pixmath::kJAdd << 8)) >> 32);
+}
+// accumulators whose byte 2 is the component (img_yuv_rgb.c:142-147).  k0 = the rounding constant plus the +16 / +128, held
+// in a register the compiler cannot see through (opaque_const): as an immediate it takes the addend slot of the first
+// multiply-add, the coefficient then needs a register that the result overwrites, and every chain re-loads it (60 MOV per
+// trip).
+__device__ __forceinline__ uint32_t opaque_const(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t iacc_y(uint32_t r, uint32_t g, uint32_t b, uint32_t k0) { return r * 16829u + (g * 33039u + (b * 6416u + k0)); }
+__device__ __forceinline__ uint32_t iacc_u(uint32_t r, uint32_t g, uint32_t b, uint32_t k0)
+{
+    return (uint32_t)((int)r * -9714 + ((int)g * -19070 + ((int)b * 28784 + (int)k0)));
+}
+__device__ __forceinline__ uint32_t iacc_v(uint32_t r, uint32_t g, uint32_t b, uint32_t k0)
+{
+    return (uint32_t)((int)r * 28784 + ((int)g * -24103 + ((int)b * -4681 + (int)k0)));
+}
+
 template <int DST>
 __global__ void __launch_bounds__(256, 3) k_yuv420_rgb_yuv(FastParams p)
 {
@@ -1096,6 +1134,9 @@ __global__ void __launch_bounds__(256, 3) k_yuv420_rgb_yuv(FastParams p)
     const int unit = blockIdx.z * blockDim.x + threadIdx.x;
     if (unit >= p.upr) return;
     constexpr int SL = L_RGBA;          // convert_row<..., 4, false>: R, G, B in bytes 0..2 of each pixel word
+    (void)SL;
+    const uint32_t ky = opaque_const(32768u + (16u << 16)), kc = opaque_const(32768u + (128u << 16));
+    (void)ky; (void)kc;
     for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
         const uint8_t *yp = Ys + (size_t)(2 * rp) * p.w + unit * 16;
         const uint4 a = ldg128(yp), b = ldg128(yp + p.w);
@@ -1108,38 +1149,52 @@ __global__ void __launch_bounds__(256, 3) k_yuv420_rgb_yuv(FastParams p)
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const uint32_t yw[4] = {r ? b.x : a.x, r ? b.y : a.y, r ? b.z : a.z, r ? b.w : a.w};
-            uint32_t px[16], ay[16];
+            uint32_t ay[16], ua[16], va[16];       // component accumulators; only the sampled positions are computed
+            (void)ua; (void)va;
+#if ACGPU_FUSED_IMAD
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t sel = 0x10u << (8 * (k & 3));
+                const uint32_t R = channel_int<kBiasRB>(yw[k >> 2], sel, cr[k >> 1]);
+                const uint32_t G = channel_int<kBiasG>(yw[k >> 2], sel, cg[k >> 1]);
+                const uint32_t B = channel_int<kBiasRB>(yw[k >> 2], sel, cb[k >> 1]);
+                ay[k] = iacc_y(R, G, B, ky);
+                if (DST == D444) { ua[k] = iacc_u(R, G, B, kc); va[k] = iacc_v(R, G, B, kc); }
+                else if (DST == D422) { if (k & 1) va[k] = iacc_v(R, G, B, kc); else ua[k] = iacc_u(R, G, B, kc); }
+                else if (r == 0 && !(k & 1)) ua[k] = iacc_u(R, G, B, kc);        // D420: U at (even x, even y)
+                else if (r == 1 && (k & 1)) va[k] = iacc_v(R, G, B, kc);         //       V at (odd x, odd y)
+            }
+#else
+            uint32_t px[16];
             convert_row<S420, false, 4, false>(yw, cr, cg, cb, px);
 #pragma unroll
-            for (int k = 0; k < 16; k++) ay[k] = acc_y<SL>(px[k]);
+            for (int k = 0; k < 16; k++) {
+                ay[k] = acc_y<SL>(px[k]);
+                if (DST == D444) { ua[k] = acc_u<SL>(px[k]); va[k] = acc_v<SL>(px[k]); }
+                else if (DST == D422) { if (k & 1) va[k] = acc_v<SL>(px[k]); else ua[k] = acc_u<SL>(px[k]); }
+                else if (r == 0 && !(k & 1)) ua[k] = acc_u<SL>(px[k]);
+                else if (r == 1 && (k & 1)) va[k] = acc_v<SL>(px[k]);
+            }
+#endif
             const size_t row = (size_t)(2 * rp + r);
             stg128(Y + row * p.w + unit * 16,
                    make_uint4(pack_b2x4(ay[0], ay[1], ay[2], ay[3]), pack_b2x4(ay[4], ay[5], ay[6], ay[7]),
                               pack_b2x4(ay[8], ay[9], ay[10], ay[11]), pack_b2x4(ay[12], ay[13], ay[14], ay[15])));
             if (DST == D422) {          // U at even x, V at odd x of every row (img_yuv_rgb.c:166)
-                uint32_t ua[8], va[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) { ua[k] = acc_u<SL>(px[2 * k]); va[k] = acc_v<SL>(px[2 * k + 1]); }
-                stg64(U + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[1], ua[2], ua[3]), pack_b2x4(ua[4], ua[5], ua[6], ua[7])));
-                stg64(V + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[0], va[1], va[2], va[3]), pack_b2x4(va[4], va[5], va[6], va[7])));
+                stg64(U + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[2], ua[4], ua[6]), pack_b2x4(ua[8], ua[10], ua[12], ua[14])));
+                stg64(V + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[1], va[3], va[5], va[7]), pack_b2x4(va[9], va[11], va[13], va[15])));
             } else if (DST == D420) {   // U at (even x, even y), V at (odd x, odd y) (:162)
-                uint32_t ca[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) ca[k] = r ? acc_v<SL>(px[2 * k + 1]) : acc_u<SL>(px[2 * k]);
-                stg64((r ? V : U) + (size_t)rp * (p.w >> 1) + unit * 8,
-                      make_uint2(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7])));
+                if (r == 0)
+                    stg64(U + (size_t)rp * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[2], ua[4], ua[6]), pack_b2x4(ua[8], ua[10], ua[12], ua[14])));
+                else
+                    stg64(V + (size_t)rp * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[1], va[3], va[5], va[7]), pack_b2x4(va[9], va[11], va[13], va[15])));
             } else {                    // D444: every pixel
-                uint32_t ca[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) ca[k] = acc_u<SL>(px[k]);
                 stg128(U + row * p.w + unit * 16,
-                       make_uint4(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7]),
-                                  pack_b2x4(ca[8], ca[9], ca[10], ca[11]), pack_b2x4(ca[12], ca[13], ca[14], ca[15])));
-#pragma unroll
-                for (int k = 0; k < 16; k++) ca[k] = acc_v<SL>(px[k]);
+                       make_uint4(pack_b2x4(ua[0], ua[1], ua[2], ua[3]), pack_b2x4(ua[4], ua[5], ua[6], ua[7]),
+                                  pack_b2x4(ua[8], ua[9], ua[10], ua[11]), pack_b2x4(ua[12], ua[13], ua[14], ua[15])));
                 stg128(V + row * p.w + unit * 16,
-                       make_uint4(pack_b2x4(ca[0], ca[1], ca[2], ca[3]), pack_b2x4(ca[4], ca[5], ca[6], ca[7]),
-                                  pack_b2x4(ca[8], ca[9], ca[10], ca[11]), pack_b2x4(ca[12], ca[13], ca[14], ca[15])));
+                       make_uint4(pack_b2x4(va[0], va[1], va[2], va[3]), pack_b2x4(va[4], va[5], va[6], va[7]),
+                                  pack_b2x4(va[8], va[9], va[10], va[11]), pack_b2x4(va[12], va[13], va[14], va[15])));
             }
         }
     }
