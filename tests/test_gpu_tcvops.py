@@ -112,6 +112,11 @@ def test_full_size_planes(ac, tcv, bpp):
             ("reduce", (3, 3), tcv.reduce(src, w, h, bpp, 3, 3)),
             ("reduce", (4, 4), tcv.reduce(src, w, h, bpp, 4, 4)),
             ("reduce", (5, 2), tcv.reduce(src, w, h, bpp, 5, 2)),
+            ("reduce", (5, 5), tcv.reduce(src, w, h, bpp, 5, 5)),
+            ("reduce", (6, 1), tcv.reduce(src, w, h, bpp, 6, 1)),
+            ("reduce", (7, 3), tcv.reduce(src, w, h, bpp, 7, 3)),      # 1920 / 7 = 274: not on the 16-pixel grid -> gather kernel
+            ("reduce", (8, 4), tcv.reduce(src, w, h, bpp, 8, 4)),
+            ("reduce", (9, 2), tcv.reduce(src, w, h, bpp, 9, 2)),
             ("clip", (3, 5, 1, 1, 16), tcv.clip(src, w, h, bpp, 3, 5, 1, 1, black=16)),
             ("clip", (1, 0, 0, 0, 16), tcv.clip(src, w, h, bpp, 1, 0, 0, 0, black=16)),
             ("clip", (13, 2, 0, 3, 16), tcv.clip(src, w, h, bpp, 13, 2, 0, 3, black=16)),

@@ -67,7 +67,10 @@ for bpp in ((a.bpp,) if a.bpp else (1, 3)):
     run(f"reduce 2x2            {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 2, 2, fb, fb // 4, n, st), n, fb // 4, fb // 4)
     run(f"reduce 3x3            {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 3, 3, fb, fb // 9, n, st), n, fb // 9, fb // 9)
     run(f"reduce 4x4            {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 4, 4, fb, fb // 16, n, st), n, fb // 16, fb // 16)
-    run(f"reduce 5x5 (gather)   {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 5, 5, fb, (w // 5) * (h // 5) * bpp, n, st), n, (w // 5) * (h // 5) * bpp, (w // 5) * (h // 5) * bpp)
+    run(f"reduce 5x5            {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 5, 5, fb, (w // 5) * (h // 5) * bpp, n, st), n, (w // 5) * (h // 5) * bpp, (w // 5) * (h // 5) * bpp)
+    run(f"reduce 8x8 (gather)   {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 8, 8, fb, (w // 8) * (h // 8) * bpp, n, st), n, (w // 8) * (h // 8) * bpp, (w // 8) * (h // 8) * bpp)
+    run(f"reduce 6x6            {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 6, 6, fb, (w // 6) * (h // 6) * bpp, n, st), n, (w // 6) * (h // 6) * bpp, (w // 6) * (h // 6) * bpp)
+    run(f"reduce 7x7 (gather)   {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 7, 7, fb, (w // 7) * (h // 7) * bpp, n, st), n, (w // 7) * (h // 7) * bpp, (w // 7) * (h // 7) * bpp)
     run(f"reduce 1x2            {t}", lambda: lib.acgpu_reduce_batch(S, D, w, h, bpp, 1, 2, fb, fb // 2, n, st), n, fb // 2, fb // 2)
     run(f"flip_v                {t}", lambda: lib.acgpu_flip_v_batch(S, D, w, h, bpp, fb, fb, n, st), n, fb, fb)
     run(f"flip_v in place       {t}", lambda: lib.acgpu_flip_v_batch(S, S, w, h, bpp, fb, fb, n, st), n, fb, fb)

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_w2(const uint8_t *src0, siz
     }
 }
 
-// reduce_w == RW (3 or 4), output rows a multiple of 16 pixels, aligned planes: a thread turns 16*RW source pixels
+// reduce_w == RW (3 .. 6), output rows a multiple of 16 pixels, aligned planes: a thread turns 16*RW source pixels
 // (RW*BPP 128-bit loads) into 16 destination pixels (BPP 128-bit stores); which source byte lands where is known at
 // compile time, so the selection is a handful of byte permutes instead of one byte load per destination byte.
 template <int BPP, int RW>
@@ -717,12 +717,18 @@ bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t d
         ACGPU_CHECK_LAUNCH("k_reduce_w2");
         return true;
     }
-    if ((rw == 3 || rw == 4) && ow % 16 == 0 && ((size_t)w * Bpp) % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes)) {
+    if (rw >= 3 && rw <= 6 && ow % 16 == 0 && ((size_t)w * Bpp) % 16 == 0 && al16p(src, spitch, nframes) && al16p(dst, dpitch, nframes)) {
+        // a kept row is fetched whole (every 32-byte sector of it holds kept pixels up to ratio 32 at Bpp 1), so whole-row
+        // 128-bit loads + compile-time byte selection are also the DRAM-optimal form -- up to ratio 6: a lane's loads lie
+        // 16 * ratio bytes from its neighbour's, so each load instruction touches 4 * ratio cache lines, and at 8 that costs
+        // more than the byte gather does (8x8 luma: 0.30 of the copy rate in DRAM bytes against ~0.6; 5x5: 0.92 against 0.62)
         const dim3 gn = grid_for((uint64_t)(ow / 16) * oh, nframes);
-        if (Bpp == 1 && rw == 3) k_reduce_wn<1, 3><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
-        else if (Bpp == 1) k_reduce_wn<1, 4><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
-        else if (rw == 3) k_reduce_wn<3, 3><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
-        else k_reduce_wn<3, 4><<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh);
+        auto go = [&](auto kern) { kern<<<gn, kThreads, 0, st>>>(src, spitch, dst, dpitch, w, ow, oh, rh); };
+#define ACGPU_REDUCE_CASE(R) case R: if (Bpp == 1) go(k_reduce_wn<1, R>); else go(k_reduce_wn<3, R>); break;
+        switch (rw) {
+            ACGPU_REDUCE_CASE(3) ACGPU_REDUCE_CASE(4) ACGPU_REDUCE_CASE(5) ACGPU_REDUCE_CASE(6)
+        }
+#undef ACGPU_REDUCE_CASE
         note_launch();
         ACGPU_CHECK_LAUNCH("k_reduce_wn");
         return true;
