@@ -86,8 +86,8 @@ bool blend_launch(const uint8_t *s1, const uint8_t *s2, uint8_t *d, size_t bytes
                   uint32_t w1, uint32_t w2, int op, cudaStream_t st);
 bool resize_h_row_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint16_t *d_off,
                          const uint32_t *d_wgt, int width, int new_w, int rows, int Bpp, int nframes, cudaStream_t st);
-bool resize_h_win_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint32_t *d_meta,
-                         const uint32_t *d_wgt, int width, int new_w, int rows, int Bpp, int nframes, cudaStream_t st);
+bool resize_h_win_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint2 *d_meta,
+                         const uint32_t *d_wgt, int width, int new_w, int rows, int Bpp, bool narrow, int nframes, cudaStream_t st);
 bool resize_h_vectorisable(const uint8_t *src, size_t spitch, const uint8_t *dst, size_t dpitch, int width, int new_w, int Bpp);
 bool resize_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
                      const int32_t *d_source, const uint32_t *d_w1, const uint32_t *d_w2,

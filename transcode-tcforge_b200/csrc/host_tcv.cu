@@ -298,24 +298,31 @@ int acgpu_resize_batch(const uint8_t *src, uint8_t *dest, int width, int height,
                     }
             const uint32_t *dwgt = static_cast<const uint32_t *>(device_blob(c, wgt.data(), wgt.size() * sizeof(uint32_t), st));
             if (!dwgt) return 0;
-            // window form: the four first taps of every output word within 8 source bytes (any ratio up to ~2:1)
-            std::vector<uint32_t> meta(off.size() / 4);
-            bool windowed = tls.force_tier != 1;
+            // window form: the four first taps of every output word within 8 source bytes (any ratio up to ~2:1);
+            // narrow: the second taps that carry weight lie inside those 8 bytes too (a second tap of weight 0 may select
+            // any byte: its selector is clamped into the window)
+            std::vector<uint2> meta(off.size() / 4);
+            bool windowed = tls.force_tier != 1, narrow = true;
             for (size_t ow = 0; ow < meta.size() && windowed; ow++) {
                 uint32_t lo = off[4 * ow], hi = lo;
                 for (int j = 1; j < 4; j++) { lo = std::min<uint32_t>(lo, off[4 * ow + j]); hi = std::max<uint32_t>(hi, off[4 * ow + j]); }
                 if (hi - lo > 7) { windowed = false; break; }
-                uint32_t sel = 0;
-                for (int j = 0; j < 4; j++) sel |= (off[4 * ow + j] - lo) << (4 * j);
-                meta[ow] = lo | (sel << 16);
+                uint32_t selA = 0, selB = 0;
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t t = off[4 * ow + j] - lo, t2 = t + (uint32_t)Bpp;
+                    selA |= t << (4 * j);
+                    if (t2 > 7 && (wgt[4 * ow + j] >> 16) != 0) narrow = false;
+                    selB |= (t2 > 7 ? 7u : t2) << (4 * j);
+                }
+                meta[ow] = make_uint2(lo | (selA << 16), selB);
             }
             if (windowed) {
-                const uint32_t *dmeta = static_cast<const uint32_t *>(device_blob(c, meta.data(), meta.size() * sizeof(uint32_t), st));
+                const uint2 *dmeta = static_cast<const uint2 *>(device_blob(c, meta.data(), meta.size() * sizeof(uint2), st));
                 if (!dmeta) return 0;
                 for (int f0 = 0; f0 < nframes; f0 += 32768) {
                     const int nf = nframes - f0 < 32768 ? nframes - f0 : 32768;
                     if (!resize_h_win_launch(src + (size_t)f0 * sp_, sp_, dest + (size_t)f0 * dp_, dp_, dmeta, dwgt, width, new_w,
-                                             new_h, Bpp, nf, st))
+                                             new_h, Bpp, narrow, nf, st))
                         return 0;
                 }
                 return 1;

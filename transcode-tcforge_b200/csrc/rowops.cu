@@ -234,13 +234,50 @@ __global__ void __launch_bounds__(256) k_resize_h_row(const uint8_t *src, size_t
 
 // Window form of the same kernel (the default whenever the table allows it, i.e. for every ratio up to ~2:1): the four
 // first taps of an output word lie within 8 consecutive source bytes, and the second taps are those bytes + Bpp.  So
-// instead of eight byte gathers the thread reads four aligned shared-memory words at the window base, funnel-shifts them
-// to the base's byte alignment (and by a further Bpp bytes for the second taps), picks the taps with one PRMT each using a
-// host-built selector, interleaves them with two more PRMTs and blends two outputs per word with dp2a.lo / dp2a.hi.
-// meta[ow] = window base (source byte offset in the row, 16 bits) | PRMT selector (16 bits); weights as above.
-template <int BPP>
+// instead of eight byte gathers the thread reads three or four aligned shared-memory words at the window base, funnel-shifts
+// them to the base's byte alignment, picks the taps with one PRMT each using host-built selectors, interleaves them with two
+// more PRMTs and blends two outputs per word with dp2a.lo / dp2a.hi.
+// meta[ow] = { window base (source byte offset in the row, 16 bits) | selector of the first taps (16 bits),
+//              selector of the second taps (NARROW only) }; weights as above.
+// NARROW: every second tap that carries weight also lies inside the window's 8 bytes (always when enlarging a Bpp 1 plane,
+// and up to ~2:1 when shrinking one), so both tap sets come out of the same two shifted words: three shared loads, two
+// funnel shifts and two PRMTs per row instead of four, five and two.
+// The kernel is bound by instruction issue (ncu: issue 78 %, ALU pipe 71 % enlarging 1920 -> 2560), so the shape of the row
+// loop matters: rows of a full block are unrolled without per-row branches, the shared window address is formed once per
+// output word (shared-space loads through a 32-bit address; the generic form re-derived the shared base in every row), and
+// the store pointer advances by the row pitch.
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+template <int BPP, bool NARROW>
+__device__ __forceinline__ uint32_t resize_word(uint32_t saddr, uint32_t sh, uint32_t selA, uint32_t selB, const uint4 &w4)
+{
+    const uint32_t w0 = lds32(saddr), w1 = lds32(saddr + 4), w2 = lds32(saddr + 8);
+    const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
+    uint32_t A, B;
+    if (NARROW) {
+        A = __byte_perm(W0, W1, selA);
+        B = __byte_perm(W0, W1, selB);
+    } else {
+        const uint32_t w3 = BPP == 1 ? 0u : lds32(saddr + 12);
+        const uint32_t W2 = __funnelshift_r(w2, w3, sh);
+        A = __byte_perm(W0, W1, selA);
+        B = __byte_perm(__funnelshift_r(W0, W1, 8 * BPP), __funnelshift_r(W1, W2, 8 * BPP), selA);
+    }
+    const uint32_t X0 = __byte_perm(A, B, 0x5140), X1 = __byte_perm(A, B, 0x7362);
+    uint32_t v0, v1, v2, v3;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(v0) : "r"(w4.x), "r"(X0), "r"(32768u));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(v1) : "r"(w4.y), "r"(X0), "r"(32768u));
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(v2) : "r"(w4.z), "r"(X1), "r"(32768u));
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(v3) : "r"(w4.w), "r"(X1), "r"(32768u));
+    return __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410);
+}
+template <int BPP, bool NARROW>
 __global__ void __launch_bounds__(256) k_resize_h_win(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch,
-                                                     const uint32_t *__restrict__ meta, const uint32_t *__restrict__ twgt,
+                                                     const uint2 *__restrict__ meta, const uint32_t *__restrict__ twgt,
                                                      int src_row_bytes, int dst_row_bytes, int rows)
 {
     extern __shared__ uint4 s_row[];
@@ -252,29 +289,26 @@ __global__ void __launch_bounds__(256) k_resize_h_win(const uint8_t *src, size_t
     for (int c = threadIdx.x; c < schunks; c += blockDim.x) cp_async16(&s_row[c], s + (size_t)c * 16);
     cp_async_wait_all();
     __syncthreads();
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_row);
-    const int wpr = dst_row_bytes >> 2, swpr = src_row_bytes >> 2;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_row);
+    const int wpr = dst_row_bytes >> 2;
     for (int ow = threadIdx.x; ow < wpr; ow += blockDim.x) {
-        const uint32_t m = __ldg(meta + ow);
+        const uint2 m = __ldg(meta + ow);
         const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(twgt) + ow);      // four weight pairs
-        const uint32_t base = m & 0xFFFFu, sel = m >> 16, sh = (base & 3u) * 8;
-        const uint32_t *rw = sw + (base >> 2);
+        const uint32_t base = m.x & 0xFFFFu, selA = m.x >> 16, selB = m.y, sh = (base & 3u) * 8;
+        uint32_t saddr = sbase + (base & ~3u);
+        uint32_t *out = reinterpret_cast<uint32_t *>(d) + ow;
+        if (nrows == kResizeRows) {
 #pragma unroll
-        for (int r = 0; r < kResizeRows; r++) {
-            if (r < nrows) {
-                const uint32_t *q = rw + (size_t)r * swpr;
-                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = BPP == 1 ? 0u : q[3];
-                const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh), W2 = __funnelshift_r(w2, w3, sh);
-                const uint32_t A = __byte_perm(W0, W1, sel);
-                const uint32_t B = __byte_perm(__funnelshift_r(W0, W1, 8 * BPP), __funnelshift_r(W1, W2, 8 * BPP), sel);
-                const uint32_t X0 = __byte_perm(A, B, 0x5140), X1 = __byte_perm(A, B, 0x7362);
-                uint32_t v0, v1, v2, v3;
-                asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(v0) : "r"(w4.x), "r"(X0), "r"(32768u));
-                asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(v1) : "r"(w4.y), "r"(X0), "r"(32768u));
-                asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(v2) : "r"(w4.z), "r"(X1), "r"(32768u));
-                asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(v3) : "r"(w4.w), "r"(X1), "r"(32768u));
-                __stcs(reinterpret_cast<uint32_t *>(d + (size_t)r * dst_row_bytes) + ow,
-                       __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410));
+            for (int r = 0; r < kResizeRows; r++) {
+                __stcs(out, resize_word<BPP, NARROW>(saddr, sh, selA, selB, w4));
+                saddr += (uint32_t)src_row_bytes;
+                out += wpr;
+            }
+        } else {
+            for (int r = 0; r < nrows; r++) {
+                __stcs(out, resize_word<BPP, NARROW>(saddr, sh, selA, selB, w4));
+                saddr += (uint32_t)src_row_bytes;
+                out += wpr;
             }
         }
     }
@@ -383,13 +417,14 @@ bool resize_h_row_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t
     return true;
 }
 
-bool resize_h_win_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint32_t *d_meta,
-                         const uint32_t *d_wgt, int width, int new_w, int rows, int Bpp, int nframes, cudaStream_t st)
+bool resize_h_win_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, const uint2 *d_meta,
+                         const uint32_t *d_wgt, int width, int new_w, int rows, int Bpp, bool narrow, int nframes, cudaStream_t st)
 {
     const int srb = width * Bpp, drb = new_w * Bpp;
     if (rows <= 0 || nframes <= 0) return true;
     const size_t smem = (size_t)srb * kResizeRows + 32;        // the last window may look up to 16 bytes past the rows
-    auto kern = Bpp == 1 ? k_resize_h_win<1> : k_resize_h_win<3>;
+    auto kern = Bpp == 1 ? (narrow ? k_resize_h_win<1, true> : k_resize_h_win<1, false>)
+                         : (narrow ? k_resize_h_win<3, true> : k_resize_h_win<3, false>);
     if (smem > 48 * 1024 && !check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
         return false;
     dim3 g((unsigned)((rows + kResizeRows - 1) / kResizeRows), (unsigned)nframes);
