@@ -89,7 +89,7 @@ def test_fuzz_batched_conversions(ac, chk, chunk):
         ac.sync()
         what = f"chunk {chunk} case {case}: {F.NAMES[sf]}->{F.NAMES[df]} {w}x{h} nf={nf} aligned={aligned} tier={ac.lib.acgpu_last_kernel_tier()}"
         assert ok == 1, (what, ac.last_error())
-        tiers[ac.lib.acgpu_last_kernel_tier()] += 1
+        tiers[min(ac.lib.acgpu_last_kernel_tier(), 2)] += 1      # 3 = the tensor-map staged form of the vectorised tier
         got = ddst.download()
         want = np.full_like(got, CANARY)
         for f in range(nf):
@@ -119,7 +119,7 @@ def _tcv_call(ac, rng, op, w, h, bpp):
         nw, nh = w - a[0] - a[1], h - a[2] - a[3]
         return "clip", a + (black,), (lambda t, s: t.clip(s, w, h, bpp, *a, black=black, prefill=CANARY)), max(nw, 0) * max(nh, 0) * bpp
     if op == "reduce":
-        rw, rh = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        rw, rh = int(rng.integers(1, 9)), int(rng.integers(1, 5))      # 3 .. 6 have a kernel of their own on the 16-pixel grid
         n = w * h * bpp if (rw == 1 and rh == 1) else w * (h // rh) * bpp if rw == 1 else (w // rw) * (h // rh) * bpp
         return "reduce", (rw, rh), (lambda t, s: t.reduce(s, w, h, bpp, rw, rh, prefill=CANARY)), n
     if op == "flip_v":

@@ -342,6 +342,16 @@ def test_rows_wider_than_one_block(ac, chk):
         assert_same(got[1], chk.convert(src[::-1].copy(), sf, df, w, h, pad=0)[1], f"wide {F.NAMES[sf]}->{F.NAMES[df]} #2")
 
 
+def test_full_8k_frames(ac, chk):
+    """7680x4320: 33 M pixels per frame (132 MB as 32-bit RGB) -- the largest size of the sweeps, compared byte for byte."""
+    w, h = 7680, 4320
+    for sf, df in [(F.IMG_YUV420P, F.IMG_RGB24), (F.IMG_RGB24, F.IMG_YUV422P), (F.IMG_YUY2, F.IMG_YUV420P), (F.IMG_YUV444P, F.IMG_BGRA32)]:
+        src = ck.random_frame(sf, w, h, seed=88)
+        got = ac.convert_batch(src[None, :], sf, df, w, h)[0]
+        assert ac.lib.acgpu_last_kernel_tier() >= 2
+        assert_same(got, chk.convert(src, sf, df, w, h, pad=0)[1], f"8K {F.NAMES[sf]}->{F.NAMES[df]}")
+
+
 @pytest.mark.parametrize("mode", ["1", "2"])
 def test_bulk_async_staged_variants_are_bit_exact(mode):
     """Tier 3b/3c (ACGPU_TMA=1/2: planar sources staged by cp.async.bulk + mbarrier, optionally bulk stores too) are

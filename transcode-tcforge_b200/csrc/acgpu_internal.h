@@ -96,6 +96,28 @@ bool resize_h_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpi
 // libtcvideo plane operations (tcvops.cu).
 // Window copy: destination row y shows bytes [sxb, sxb+cn) of source row y*row_mul + row_add at its bytes [cl, cl+cn)
 // and the fill byte elsewhere (also in rows whose source row is outside [0, srows)).
+// x / d for any 32-bit x without a division instruction: m = floor(2^(32+s) / d) (capped at 2^32 - 1), s = floor(log2 d); the
+// multiply-high estimate is at most one too small, one compare fixes it.  Built on the host, used by the kernels.
+struct FastDiv {
+    uint32_t d, m, s;
+#ifdef __CUDACC__
+    __device__ __forceinline__ void divmod(uint32_t x, uint32_t &q, uint32_t &r) const
+    {
+        q = __umulhi(x, m) >> s;
+        r = x - q * d;
+        if (r >= d) { q++; r -= d; }
+    }
+#endif
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f{d ? d : 1u, 0, 0};
+    while ((2u << f.s) <= f.d && f.s < 31) f.s++;
+    const uint64_t m = ((uint64_t)1 << (32 + f.s)) / f.d;
+    f.m = m > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)m;
+    return f;
+}
+
 struct TcvWindow {
     const uint8_t *src;
     size_t   spitch;
@@ -107,7 +129,7 @@ struct TcvWindow {
     uint32_t cl, cn, sxb;
     uint32_t fill;                // fill byte replicated into all four bytes
     int      vec;                 // set by the launcher: destination chunks are 16-byte aligned
-    uint32_t div_m, div_s;        // set by the launcher: off / dBpl as a multiply-high (tcvops.cu window_row_of)
+    FastDiv  row_div;             // set by the launcher: off / dBpl
 };
 bool tcv_window_launch(TcvWindow p, int nframes, cudaStream_t st);
 bool tcv_reduce_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_t dpitch, int w, int ow, int oh, int rw, int rh,

@@ -61,14 +61,7 @@ __device__ __forceinline__ uint32_t window_byte(const TcvWindow &p, const uint8_
     return src[(size_t)sr * p.sBpl + p.sxb + (xb - p.cl)];
 }
 
-// off / dBpl without a division instruction: the launcher supplies m = floor(2^(32+s) / dBpl) (capped at 2^32 - 1) with
-// s = floor(log2 dBpl); the estimate is at most one too small for every 32-bit off, one compare fixes it.
-__device__ __forceinline__ void window_row_of(const TcvWindow &p, uint32_t off, uint32_t &y, uint32_t &xb)
-{
-    y = __umulhi(off, p.div_m) >> p.div_s;
-    xb = off - y * p.dBpl;
-    if (xb >= p.dBpl) { y++; xb -= p.dBpl; }
-}
+__device__ __forceinline__ void window_row_of(const TcvWindow &p, uint32_t off, uint32_t &y, uint32_t &xb) { p.row_div.divmod(off, y, xb); }
 
 // Bytes [sh, sh + 16) of the 32 bytes lo | hi, sh = 0..15, without a branch: drop two words, drop one word, shift by bytes.
 __device__ __forceinline__ uint4 shift16(const uint4 &lo, const uint4 &hi, uint32_t sh)
@@ -549,7 +542,8 @@ constexpr int kAaTableWords = 1024 * 32;
 
 template <int BPP, int NG, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_antialias_vec(const uint8_t *src0, size_t spitch, uint8_t *dst0, size_t dpitch,
-                                                              const uint32_t *tables, uint32_t w, uint32_t h, uint32_t nframes)
+                                                              const uint32_t *tables, uint32_t w, uint32_t h, uint32_t nframes,
+                                                              FastDiv div_chunks, FastDiv div_upr)
 {
     constexpr int W = BPP * NG, PX = 4 * NG;                // words / pixels per thread
     extern __shared__ __align__(16) uint32_t s_dyn[];
@@ -576,15 +570,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_antialias_vec(const uint8_t *src
         }
     };
     for (uint32_t c = blockIdx.x * (THREADS / 32) + warp; c < chunks; c += gridDim.x * (THREADS / 32)) {     // warp-uniform
-        const uint32_t frame = c / chunks_per_frame, i = (c - frame * chunks_per_frame) * 32 + lane;
+        uint32_t frame, cf;
+        div_chunks.divmod(c, frame, cf);
+        const uint32_t i = cf * 32 + lane;
         const uint8_t *src = src0 + (size_t)frame * spitch;
         uint8_t *dst = dst0 + (size_t)frame * dpitch;
         uint32_t S[W], any = 0, y = 0, u = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) S[k] = 0;
         if (i < n) {
-            y = i / upr;
-            u = i - y * upr;
+            div_upr.divmod(i, y, u);
             const uint32_t *cw = reinterpret_cast<const uint32_t *>(src) + (size_t)y * wpr + (size_t)u * W;
             uint32_t C[W];
             load_words(cw, C);
@@ -688,10 +683,7 @@ bool tcv_window_launch(TcvWindow p, int nframes, cudaStream_t st)
     p.vec = al16p(p.dst, p.dpitch, nframes) ? 1 : 0;
     const uint64_t N = (uint64_t)p.dBpl * p.drows;
     if (N == 0) return true;
-    uint32_t s = 0;
-    while ((2u << s) <= p.dBpl && s < 31) s++;
-    const uint64_t m = ((uint64_t)1 << (32 + s)) / p.dBpl;
-    p.div_s = s; p.div_m = m > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)m;
+    p.row_div = make_fastdiv(p.dBpl);
     // every whole chunk's source 16-byte aligned?  (chunk at byte xb of destination row y reads source row
     // y * row_mul + row_add from byte sxb + xb - cl on)
     const bool aligned = p.vec && p.sBpl % 16 == 0 && p.dBpl % 16 == 0 && (nframes <= 1 || p.spitch % 16 == 0)
@@ -792,7 +784,8 @@ bool tcv_antialias_launch(const uint8_t *src, size_t spitch, uint8_t *dst, size_
             const uint64_t chunks = (uint64_t)chunks_per_frame * nframes;
             const uint64_t want = (chunks + threads / 32 - 1) / (threads / 32);
             const unsigned gx = (unsigned)(want < (uint64_t)sm_count() ? want : (uint64_t)sm_count());
-            kern<<<gx, threads, smem, st>>>(src, spitch, dst, dpitch, d_tables, (uint32_t)w, (uint32_t)h, (uint32_t)nframes);
+            kern<<<gx, threads, smem, st>>>(src, spitch, dst, dpitch, d_tables, (uint32_t)w, (uint32_t)h, (uint32_t)nframes,
+                                            make_fastdiv(chunks_per_frame), make_fastdiv((uint32_t)(w / (wide ? 16 : 4))));
             return true;
         };
         bool ok;
