@@ -3,7 +3,7 @@
 // The end-to-end numbers of bench.py are bounded by pinned-memory copies.  On the 8-GPU box the aggregate stalls near
 // 115 GB/s of host traffic, far below 8 PCIe Gen5 links; this probe separates the candidates:
 //   --mode threads|procs      one process driving every GPU from its own thread, or one process per GPU (fork before CUDA)
-//   --mem hostalloc|register|hugetlb|thp
+//   --mem hostalloc|wc|register|hugetlb|thp
 //                             cudaHostAlloc, or malloc'd / MAP_HUGETLB / madvise(MADV_HUGEPAGE) memory + cudaHostRegister
 //   --dir h2d|d2h|both        one direction alone or both at once (two streams per GPU)
 //   --region MB               pinned bytes per GPU and direction that the copies walk through
@@ -74,12 +74,14 @@ static void bind_to_node(int node)
     sched_setaffinity(0, sizeof(set), &set);
 }
 
-static void *host_mem(size_t bytes, int g, int *registered)
+static void *host_mem(size_t bytes, int g, int *registered, int is_input = 0)
 {
     void *p = NULL;
     *registered = 0;
-    if (!strcmp(mem_kind, "hostalloc")) {
-        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return NULL;
+    if (!strcmp(mem_kind, "hostalloc") || !strcmp(mem_kind, "wc")) {
+        /* wc: the UPLOAD buffers are write-combined (the CPU only writes them; the device reads them without cache snoops) */
+        const unsigned flags = cudaHostAllocPortable | (!strcmp(mem_kind, "wc") && is_input ? cudaHostAllocWriteCombined : 0);
+        if (cudaHostAlloc(&p, bytes, flags) != cudaSuccess) return NULL;
         memset(p, g + 1, bytes);
         return p;
     }
@@ -111,7 +113,7 @@ static void *gpu_worker(void *arg)
     sh->numa_node[g] = gpu_numa_node(g);
     if (use_numa) bind_to_node(sh->numa_node[g]);
     CK(cudaFree(0));
-    if (do_in)  { hin = (uint8_t *)host_mem(region, g, &reg_in);   if (!hin)  { sh->failed[g] = 1; goto out; } CK(cudaMalloc(&din, chunk)); }
+    if (do_in)  { hin = (uint8_t *)host_mem(region, g, &reg_in, 1);   if (!hin)  { sh->failed[g] = 1; goto out; } CK(cudaMalloc(&din, chunk)); }
     if (do_out) { hout = (uint8_t *)host_mem(region, g, &reg_out); if (!hout) { sh->failed[g] = 1; goto out; } CK(cudaMalloc(&dout, chunk)); }
     CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
