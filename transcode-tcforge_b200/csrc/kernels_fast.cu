@@ -1123,7 +1123,7 @@ __device__ __forceinline__ uint32_t iacc_v(uint32_t r, uint32_t g, uint32_t b, u
 }
 
 template <int DST>
-__global__ void __launch_bounds__(256, 3) k_yuv420_rgb_yuv(FastParams p)
+__global__ void __launch_bounds__(256, 4) k_yuv420_rgb_yuv(FastParams p)
 {
     __shared__ int2 s_tab[512];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = reinterpret_cast<const int2 *>(&g_tabs16)[i];
