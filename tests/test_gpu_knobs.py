@@ -27,6 +27,9 @@ ROOT = os.path.dirname(HERE)
     ({"ACGPU_TMA": "6"}, 3),               # tier 3: three-stage tensor-map loads, tensor-map stores
     ({"ACGPU_TMA": "7"}, 3),               # tier 3: three-stage tensor-map loads, LDS + STG stores
     ({"ACGPU_TMA": "8"}, 3),               # tier 3: four-stage tensor-map loads, LDS + STG stores
+    ({"ACGPU_TMA_FLAT": "0"}, 0),          # no flat tensor-map form: widths that do not fill whole warps stay on tier 2 / the row-pair form
+    ({"ACGPU_TMA_FLAT": "2"}, 0),          # the flat tensor-map form for every width it can take (1920 and 4128 too)
+    ({"ACGPU_TMA_FLAT": "2", "ACGPU_TMA_FLAT_BLOCK": "256"}, 0),
     ({"ACGPU_TMA_AUTO": "0"}, 0),          # the automatic path without the tensor-map form (tier 2 everywhere)
     ({"ACGPU_TMA_AUTO": "7"}, 0),          # tensor-map staged loads for EVERY YUV source -> RGB24 / BGR24 (two rows per trip)
 ], ids=lambda v: "-".join(f"{k[6:]}{x}" for k, x in v.items()) if isinstance(v, dict) else f"tier{v}")

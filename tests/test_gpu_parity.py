@@ -411,11 +411,12 @@ def test_colour_bars_round_trip_exactly_on_the_gpu(ac):
 def test_flat_420_mode_sizes(ac, chk):
     """Widths whose 16-pixel units do not fill whole warps use the flat 4:2:0 walk (warps straddle row pairs and the
     transposed store writes two segments): PAL 720, 704, 640, 800; plus ragged last warps."""
-    for (w, h, nf) in [(720, 576, 2), (704, 480, 1), (640, 34, 3), (800, 6, 2), (720, 4, 1)]:
+    for (w, h, nf) in [(720, 576, 2), (704, 480, 1), (640, 34, 3), (800, 6, 2), (720, 4, 1), (528, 4, 2), (1296, 12, 1), (2000, 16, 2)]:
         for df in (F.IMG_RGB24, F.IMG_BGR24, F.IMG_RGBA32, F.IMG_ABGR32):
             frames = np.stack([ck.random_frame(F.IMG_YUV420P, w, h, seed=400 + i) for i in range(nf)])
             got = ac.convert_batch(frames, F.IMG_YUV420P, df, w, h, prefill=0x3C)
-            assert ac.lib.acgpu_last_kernel_tier() == 2
+            # 24-bit destinations take the flat tensor-map staged form (tier 3) from a warp of units per row on
+            assert ac.lib.acgpu_last_kernel_tier() == (3 if df in (F.IMG_RGB24, F.IMG_BGR24) and w >= 512 else 2)
             for i in range(nf):
                 want = chk.convert(frames[i], F.IMG_YUV420P, df, w, h, prefill=0x3C, pad=0)[1]
                 assert_same(got[i], want, f"flat420 {w}x{h} -> {F.NAMES[df]} frame {i}")

@@ -989,6 +989,125 @@ bool launch_yuv420_rgb24_tma2d(const FastParams &p, int nframes, cudaStream_t st
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Flat form of the tensor-map staged loads (YUV420P -> RGB24 / BGR24): the (row pair, unit) grid is walked as one linear
+// sequence, as in the FLAT mode of k_yuv2rgb, so every warp carries 32 real units whatever the width is -- the row-pair
+// form above gives a row's last warp whatever is left (1280: 80 units on 96 lanes, 720: 45 on 64) and needs chroma rows
+// whose stride is a multiple of 16 bytes (width % 32 == 0).  Per trip a warp issues
+//   * the luma box {128 x uint32, 2 rows} at its first unit (clipped by the tensor's row end when the warp runs over it),
+//   * for a warp that straddles the end of a row pair, a second luma box at the start of the next row pair,
+//   * ONE box of 64 words per chroma plane from a FLAT view of the plane ([frame][w*h/16 x uint32]): the chroma samples of
+//     consecutive flat units are consecutive in memory across the end of a chroma row, and a flat view has no row stride
+//     to align (PAL: chroma rows of 360 bytes),
+// onto the stage's mbarrier; lanes before the split read the first luma tile, the others the second, and the row goes out
+// through the two-segment transposed store.
+__device__ __forceinline__ void tensor_load_3d_flat(void *sdst, const CUtensorMap *map, int x, int z, uint64_t *bar)
+{
+    tensor_load_3d(sdst, map, x, 0, z, bar);
+}
+template <bool SWAP, int STAGES>
+__global__ void __launch_bounds__(256, 3) k_yuv420_rgb24_tmaflat(FastParams p, const __grid_constant__ CUtensorMap mapY,
+                                                                 const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapV)
+{
+    constexpr int BPP = 3;
+    __shared__ uint32_t s_tab[512];
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    // per warp (bytes): the 1536-byte transpose buffer, STAGES input stages of 1024 (luma A) + 1024 (luma B) + 256 (U) + 256 (V), the mbarriers
+    constexpr int kOut = 512 * BPP, kInStage = 2560, kPerWarp = kOut + STAGES * kInStage + 128;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = reinterpret_cast<const uint32_t *>(&g_tabs16)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wbase = s_raw + (size_t)warp * kPerWarp;
+    uint8_t *out0 = wbase, *in0 = wbase + kOut;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + kPerWarp - 128);
+    const int frame = blockIdx.y;
+    uint8_t *dst = p.d0 + (size_t)frame * p.dpitch;
+    const uint32_t upr = (uint32_t)p.upr, total = (uint32_t)p.nrp * upr;
+    const uint32_t stride = gridDim.x * blockDim.x, qs = stride / upr, rs = stride - qs * upr;
+    uint32_t g0 = blockIdx.x * blockDim.x + warp * 32;
+    if (g0 >= total) return;
+    uint32_t rpA = g0 / upr, uA = g0 - rpA * upr;            // the trip being converted
+    uint32_t gI = g0, rpI = rpA, uI = uA;                    // the trip being requested (STAGES - 1 ahead), lane 0 only
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int st) {       // lane 0 only: requests trip (gI, rpI, uI), then advances the request cursor
+        uint8_t *b = in0 + st * kInStage;
+        const uint32_t nv = min(32u, total - gI), k = min(nv, upr - uI);
+        mbar_expect_tx(&bars[st], k < nv ? 2560u : 1536u);
+        tensor_load_3d(b, &mapY, (int)(uI * 4), (int)(2 * rpI), frame, &bars[st]);              // x in uint32 elements: 16 pixels = 4
+        if (k < nv) tensor_load_3d(b + 1024, &mapY, 0, (int)(2 * (rpI + 1)), frame, &bars[st]);
+        tensor_load_3d_flat(b + 2048, &mapU, (int)(gI * 2), frame, &bars[st]);
+        tensor_load_3d_flat(b + 2304, &mapV, (int)(gI * 2), frame, &bars[st]);
+        gI += stride; rpI += qs; uI += rs;
+        if (uI >= upr) { uI -= upr; rpI++; }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++)
+            if (gI < total) issue(s);
+    }
+    const size_t rowb = (size_t)p.w * BPP;
+    for (int it = 0; g0 < total; g0 += stride, it++) {
+        const int nvalid = (int)min(32u, total - g0);
+        const int k = (int)min((uint32_t)nvalid, upr - uA);           // lanes that still belong to row pair A
+        const int st = it % STAGES;
+        if (lane == 0 && gI < total) issue((it + STAGES - 1) % STAGES);
+        mbar_wait(&bars[st], (it / STAGES) & 1);
+        const uint8_t *b = in0 + st * kInStage;
+        const uint8_t *yt = lane < k ? b + lane * 16 : b + 1024 + (lane - k) * 16;
+        const uint4 a = *reinterpret_cast<const uint4 *>(yt), c = *reinterpret_cast<const uint4 *>(yt + 512);
+        const uint2 uu = reinterpret_cast<const uint2 *>(b + 2048)[lane], vv = reinterpret_cast<const uint2 *>(b + 2304)[lane];
+        __syncwarp();        // every lane has read this stage before lane 0 may refill it (STAGES - 1 trips from now)
+        const uint32_t y0[4] = {a.x, a.y, a.z, a.w}, y1[4] = {c.x, c.y, c.z, c.w};
+        int cr[8], cg[8], cb[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            chroma_terms<S420>(reinterpret_cast<const int2 *>(s_tab), byte_of(s < 4 ? uu.x : uu.y, s & 3),
+                               byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+        uint8_t *segA = dst + ((size_t)(2 * rpA) * p.w + (size_t)uA * 16) * BPP;
+        uint8_t *segB = dst + (size_t)(2 * (rpA + 1)) * rowb;
+        uint32_t ow[BPP * 4];
+        convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
+        store_row_rgb2<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA, segB, k, nvalid);
+        convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
+        store_row_rgb2<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA + rowb, segB + rowb, k, nvalid);
+        rpA += qs;
+        uA += rs;
+        if (uA >= upr) { uA -= upr; rpA++; }
+    }
+}
+
+template <bool SWAP>
+bool launch_yuv420_rgb24_tmaflat(const FastParams &p, int nframes, cudaStream_t st)
+{
+    constexpr int STAGES = 2;       // 2 / 3 / 4 stages: 0.92 / 0.90 / 0.88 of the copy rate (the shared memory a stage costs is occupancy)
+    CUtensorMap mY, mU, mV;
+    const uint64_t w = (uint64_t)p.w, h = (uint64_t)p.nrp * 2, nf = (uint64_t)nframes, cbytes = w * h / 4;
+    if (!make_map3(&mY, p.s0, 4, w, h, nf, p.spitch, 128, 2) || !make_map3(&mU, p.s1, 4, cbytes, 1, nf, p.spitch, 64, 1)
+        || !make_map3(&mV, p.s2, 4, cbytes, 1, nf, p.spitch, 64, 1))
+        return false;
+    // 6.6 KB of stages per warp; blocks of four warps measured best (96 / 128 / 160 threads: 0.90 / 0.92 / 0.88)
+    static const int threads = [] { const char *e = getenv("ACGPU_TMA_FLAT_BLOCK"); const int v = e ? atoi(e) : 128; return v >= 32 && v <= 256 ? v / 32 * 32 : 128; }();
+    LaunchShape s;
+    s.block = dim3((unsigned)threads);
+    const long total = (long)p.upr * p.nrp, maxgx = (total + threads - 1) / threads;
+    long gx = ((long)sm_count() * (640 / threads) * waves(8) + nframes - 1) / nframes;
+    if (gx < 1) gx = 1;
+    if (gx > maxgx) gx = maxgx;
+    s.grid = dim3((unsigned)gx, (unsigned)nframes);
+    const size_t smem = (size_t)(s.block.x / 32) * (1536 + STAGES * 2560 + 128) + 128;
+    auto kern = k_yuv420_rgb24_tmaflat<SWAP, STAGES>;
+    if (!check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return false;
+    kern<<<s.grid, s.block, smem, st>>>(p, mY, mU, mV);
+    note_launch();
+    ACGPU_CHECK_LAUNCH("k_yuv420_rgb24_tmaflat");
+    return true;
+}
+
 template <bool SWAP>
 bool launch_tma2d_mode(int mode, const FastParams &p, int nframes, cudaStream_t st)
 {
@@ -1322,17 +1441,27 @@ bool convert_tma_auto(const ConvertArgs &a)
     if (sd.kind != K_PLANAR && sd.kind != K_PACKED) return false;
     FastParams p;
     if (!fast_domain(a, &p) || p.ragged420 || a.h % 2) return false;
-    // tensor-map strides are multiples of 16 bytes: the narrowest plane's rows decide
-    const int wmod = a.srcfmt == IMG_YUV411P ? 64 : sd.kind == K_PACKED || a.srcfmt == IMG_YUV444P ? 16 : 32;
-    if (a.w % wmod) return false;
-    const int upr = a.w / 16, lanes_row = ((upr + 31) / 32) * 32;
-    if (upr * 10 < lanes_row * 8 || upr > 256 * 65535) return false;
     if (!encode_tiled_fn()) return false;
     // a geometry the tensor-map encoder refuses is not an error of the call: nothing was launched, tier 2 takes it
     auto soft = [](bool launched) {
         if (!launched && t_encode_failed) { t_encode_failed = false; set_error("%s", ""); }
         return launched;
     };
+    const int upr = a.w / 16, lanes_row = ((upr + 31) / 32) * 32;
+    // YUV420P whose rows leave more than a tenth of the row-pair form's lanes idle, or whose chroma rows that form cannot
+    // describe (width % 32 != 0): the flat form -- 0.90-0.92 of the copy rate at every width measured (PAL 0.83 -> 0.92, 1280x720
+    // 0.87 -> 0.92, 640x480 / 800x600 / 1600x900 0.83 -> 0.90), where the row-pair form reaches 0.96-0.99 on full warps
+    // (1920, 2560, 3840).  $ACGPU_TMA_FLAT: 0 never, 1 (default) that rule, 2 every width it can take.
+    static const int flat_mode = [] { const char *e = getenv("ACGPU_TMA_FLAT"); return e ? atoi(e) : 1; }();
+    if (a.srcfmt == IMG_YUV420P && (enabled & 1) && flat_mode && upr >= 32 && (uint64_t)upr * (uint64_t)(a.h / 2) < 0x7FFFFFFFu
+        && (flat_mode >= 2 || a.w % 32 != 0 || upr * 10 < lanes_row * 9)) {
+        return a.dstfmt == IMG_BGR24 ? soft(launch_yuv420_rgb24_tmaflat<true>(p, a.nframes, a.stream))
+                                     : soft(launch_yuv420_rgb24_tmaflat<false>(p, a.nframes, a.stream));
+    }
+    // tensor-map strides are multiples of 16 bytes: the narrowest plane's rows decide
+    const int wmod = a.srcfmt == IMG_YUV411P ? 64 : sd.kind == K_PACKED || a.srcfmt == IMG_YUV444P ? 16 : 32;
+    if (a.w % wmod) return false;
+    if (upr * 10 < lanes_row * 8 || upr > 256 * 65535) return false;
     if (a.srcfmt == IMG_YUV420P) return (enabled & 1) && soft(tma_loads_dst(a.dstfmt, p, a.nframes, a.stream));
     const bool wins = a.srcfmt == IMG_YUV411P || (a.srcfmt == IMG_YUV422P && a.w >= 1920);
     if (!(enabled & (wins ? 2 : 4))) return false;
