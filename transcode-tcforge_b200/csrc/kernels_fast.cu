@@ -1241,6 +1241,70 @@ __device__ __forceinline__ uint32_t iacc_v(uint32_t r, uint32_t g, uint32_t b, u
     return (uint32_t)((int)r * 28784 + ((int)g * -24103 + ((int)b * -4681 + (int)k0)));
 }
 
+// One unit (16 pixels of both rows of a pair) of the fused pair: luma words a / b, chroma words uu / vv -> stores.
+template <int DST>
+__device__ __forceinline__ void fused_unit(const FastParams &p, const int2 *s_tab, const uint4 &a, const uint4 &b, const uint2 &uu,
+                                           const uint2 &vv, uint8_t *Y, uint8_t *U, uint8_t *V, int rp, int unit, uint32_t ky, uint32_t kc)
+{
+    constexpr int SL = L_RGBA;          // convert_row<..., 4, false>: R, G, B in bytes 0..2 of each pixel word
+    (void)SL; (void)ky; (void)kc;
+    int cr[8], cg[8], cb[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+        chroma_terms<S420>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t yw[4] = {r ? b.x : a.x, r ? b.y : a.y, r ? b.z : a.z, r ? b.w : a.w};
+        uint32_t ay[16], ua[16], va[16];       // component accumulators; only the sampled positions are computed
+        (void)ua; (void)va;
+#if ACGPU_FUSED_IMAD
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t sel = 0x10u << (8 * (k & 3));
+            const uint32_t R = channel_int<kBiasRB>(yw[k >> 2], sel, cr[k >> 1]);
+            const uint32_t G = channel_int<kBiasG>(yw[k >> 2], sel, cg[k >> 1]);
+            const uint32_t B = channel_int<kBiasRB>(yw[k >> 2], sel, cb[k >> 1]);
+            ay[k] = iacc_y(R, G, B, ky);
+            if (DST == D444) { ua[k] = iacc_u(R, G, B, kc); va[k] = iacc_v(R, G, B, kc); }
+            else if (DST == D422) { if (k & 1) va[k] = iacc_v(R, G, B, kc); else ua[k] = iacc_u(R, G, B, kc); }
+            else if (r == 0 && !(k & 1)) ua[k] = iacc_u(R, G, B, kc);        // D420: U at (even x, even y)
+            else if (r == 1 && (k & 1)) va[k] = iacc_v(R, G, B, kc);         //       V at (odd x, odd y)
+        }
+#else
+        uint32_t px[16];
+        convert_row<S420, false, 4, false>(yw, cr, cg, cb, px);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            ay[k] = acc_y<SL>(px[k]);
+            if (DST == D444) { ua[k] = acc_u<SL>(px[k]); va[k] = acc_v<SL>(px[k]); }
+            else if (DST == D422) { if (k & 1) va[k] = acc_v<SL>(px[k]); else ua[k] = acc_u<SL>(px[k]); }
+            else if (r == 0 && !(k & 1)) ua[k] = acc_u<SL>(px[k]);
+            else if (r == 1 && (k & 1)) va[k] = acc_v<SL>(px[k]);
+        }
+#endif
+        const size_t row = (size_t)(2 * rp + r);
+        stg128(Y + row * p.w + unit * 16,
+               make_uint4(pack_b2x4(ay[0], ay[1], ay[2], ay[3]), pack_b2x4(ay[4], ay[5], ay[6], ay[7]),
+                          pack_b2x4(ay[8], ay[9], ay[10], ay[11]), pack_b2x4(ay[12], ay[13], ay[14], ay[15])));
+        if (DST == D422) {          // U at even x, V at odd x of every row (img_yuv_rgb.c:166)
+            stg64(U + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[2], ua[4], ua[6]), pack_b2x4(ua[8], ua[10], ua[12], ua[14])));
+            stg64(V + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[1], va[3], va[5], va[7]), pack_b2x4(va[9], va[11], va[13], va[15])));
+        } else if (DST == D420) {   // U at (even x, even y), V at (odd x, odd y) (:162)
+            if (r == 0)
+                stg64(U + (size_t)rp * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[2], ua[4], ua[6]), pack_b2x4(ua[8], ua[10], ua[12], ua[14])));
+            else
+                stg64(V + (size_t)rp * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[1], va[3], va[5], va[7]), pack_b2x4(va[9], va[11], va[13], va[15])));
+        } else {                    // D444: every pixel
+            stg128(U + row * p.w + unit * 16,
+                   make_uint4(pack_b2x4(ua[0], ua[1], ua[2], ua[3]), pack_b2x4(ua[4], ua[5], ua[6], ua[7]),
+                              pack_b2x4(ua[8], ua[9], ua[10], ua[11]), pack_b2x4(ua[12], ua[13], ua[14], ua[15])));
+            stg128(V + row * p.w + unit * 16,
+                   make_uint4(pack_b2x4(va[0], va[1], va[2], va[3]), pack_b2x4(va[4], va[5], va[6], va[7]),
+                              pack_b2x4(va[8], va[9], va[10], va[11]), pack_b2x4(va[12], va[13], va[14], va[15])));
+        }
+    }
+}
+
 template <int DST>
 __global__ void __launch_bounds__(256, 4) k_yuv420_rgb_yuv(FastParams p)
 {
@@ -1252,70 +1316,13 @@ __global__ void __launch_bounds__(256, 4) k_yuv420_rgb_yuv(FastParams p)
     uint8_t *Y = p.d0 + doff, *U = p.d1 + doff, *V = p.d2 + doff;
     const int unit = blockIdx.z * blockDim.x + threadIdx.x;
     if (unit >= p.upr) return;
-    constexpr int SL = L_RGBA;          // convert_row<..., 4, false>: R, G, B in bytes 0..2 of each pixel word
-    (void)SL;
     const uint32_t ky = opaque_const(32768u + (16u << 16)), kc = opaque_const(32768u + (128u << 16));
-    (void)ky; (void)kc;
     for (int rp = blockIdx.x; rp < p.nrp; rp += gridDim.x) {
         const uint8_t *yp = Ys + (size_t)(2 * rp) * p.w + unit * 16;
         const uint4 a = ldg128(yp), b = ldg128(yp + p.w);
         const size_t co = (size_t)rp * (p.w >> 1) + unit * 8;
         const uint2 uu = ldg64(Us + co), vv = ldg64(Vs + co);
-        int cr[8], cg[8], cb[8];
-#pragma unroll
-        for (int s = 0; s < 8; s++)
-            chroma_terms<S420>(s_tab, byte_of(s < 4 ? uu.x : uu.y, s & 3), byte_of(s < 4 ? vv.x : vv.y, s & 3), cr[s], cg[s], cb[s]);
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const uint32_t yw[4] = {r ? b.x : a.x, r ? b.y : a.y, r ? b.z : a.z, r ? b.w : a.w};
-            uint32_t ay[16], ua[16], va[16];       // component accumulators; only the sampled positions are computed
-            (void)ua; (void)va;
-#if ACGPU_FUSED_IMAD
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const uint32_t sel = 0x10u << (8 * (k & 3));
-                const uint32_t R = channel_int<kBiasRB>(yw[k >> 2], sel, cr[k >> 1]);
-                const uint32_t G = channel_int<kBiasG>(yw[k >> 2], sel, cg[k >> 1]);
-                const uint32_t B = channel_int<kBiasRB>(yw[k >> 2], sel, cb[k >> 1]);
-                ay[k] = iacc_y(R, G, B, ky);
-                if (DST == D444) { ua[k] = iacc_u(R, G, B, kc); va[k] = iacc_v(R, G, B, kc); }
-                else if (DST == D422) { if (k & 1) va[k] = iacc_v(R, G, B, kc); else ua[k] = iacc_u(R, G, B, kc); }
-                else if (r == 0 && !(k & 1)) ua[k] = iacc_u(R, G, B, kc);        // D420: U at (even x, even y)
-                else if (r == 1 && (k & 1)) va[k] = iacc_v(R, G, B, kc);         //       V at (odd x, odd y)
-            }
-#else
-            uint32_t px[16];
-            convert_row<S420, false, 4, false>(yw, cr, cg, cb, px);
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                ay[k] = acc_y<SL>(px[k]);
-                if (DST == D444) { ua[k] = acc_u<SL>(px[k]); va[k] = acc_v<SL>(px[k]); }
-                else if (DST == D422) { if (k & 1) va[k] = acc_v<SL>(px[k]); else ua[k] = acc_u<SL>(px[k]); }
-                else if (r == 0 && !(k & 1)) ua[k] = acc_u<SL>(px[k]);
-                else if (r == 1 && (k & 1)) va[k] = acc_v<SL>(px[k]);
-            }
-#endif
-            const size_t row = (size_t)(2 * rp + r);
-            stg128(Y + row * p.w + unit * 16,
-                   make_uint4(pack_b2x4(ay[0], ay[1], ay[2], ay[3]), pack_b2x4(ay[4], ay[5], ay[6], ay[7]),
-                              pack_b2x4(ay[8], ay[9], ay[10], ay[11]), pack_b2x4(ay[12], ay[13], ay[14], ay[15])));
-            if (DST == D422) {          // U at even x, V at odd x of every row (img_yuv_rgb.c:166)
-                stg64(U + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[2], ua[4], ua[6]), pack_b2x4(ua[8], ua[10], ua[12], ua[14])));
-                stg64(V + row * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[1], va[3], va[5], va[7]), pack_b2x4(va[9], va[11], va[13], va[15])));
-            } else if (DST == D420) {   // U at (even x, even y), V at (odd x, odd y) (:162)
-                if (r == 0)
-                    stg64(U + (size_t)rp * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(ua[0], ua[2], ua[4], ua[6]), pack_b2x4(ua[8], ua[10], ua[12], ua[14])));
-                else
-                    stg64(V + (size_t)rp * (p.w >> 1) + unit * 8, make_uint2(pack_b2x4(va[1], va[3], va[5], va[7]), pack_b2x4(va[9], va[11], va[13], va[15])));
-            } else {                    // D444: every pixel
-                stg128(U + row * p.w + unit * 16,
-                       make_uint4(pack_b2x4(ua[0], ua[1], ua[2], ua[3]), pack_b2x4(ua[4], ua[5], ua[6], ua[7]),
-                                  pack_b2x4(ua[8], ua[9], ua[10], ua[11]), pack_b2x4(ua[12], ua[13], ua[14], ua[15])));
-                stg128(V + row * p.w + unit * 16,
-                       make_uint4(pack_b2x4(va[0], va[1], va[2], va[3]), pack_b2x4(va[4], va[5], va[6], va[7]),
-                                  pack_b2x4(va[8], va[9], va[10], va[11]), pack_b2x4(va[12], va[13], va[14], va[15])));
-            }
-        }
+        fused_unit<DST>(p, s_tab, a, b, uu, vv, Y, U, V, rp, unit, ky, kc);
     }
 }
 
