@@ -55,7 +55,7 @@ WORKLOADS = {
     "resize_1080_720_y": ("resize", 1, 0, 1920, 1080, 512),                                 # config 3 (1080 -> 720 rows)
     "process_frame_1080p": ("chain", F.IMG_YUV420P,                                         # a do_process_frame-shaped chain
                             [(pkg.CHAIN_DEINTERLACE, 5), (pkg.CHAIN_RESIZE, -80, -45), (pkg.CHAIN_GAMMA, 0.8)],
-                            1920, 1080, 128),                                               # -I 5 -B 45,80 -G 0.8: 1080p -> 720p
+                            1920, 1080, 256),                                               # -I 5 -B 45,80 -G 0.8: 1080p -> 720p
 }
 METRIC = {
     "yuv420p_rgb24_1080p": "1080p frames/s (ac_imgconvert YUV420P->RGB24)",
