@@ -1071,10 +1071,17 @@ __global__ void __launch_bounds__(256, 3) k_yuv420_rgb24_tmaflat(FastParams p, c
         uint8_t *segA = dst + ((size_t)(2 * rpA) * p.w + (size_t)uA * 16) * BPP;
         uint8_t *segB = dst + (size_t)(2 * (rpA + 1)) * rowb;
         uint32_t ow[BPP * 4];
-        convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
-        store_row_rgb2<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA, segB, k, nvalid);
-        convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
-        store_row_rgb2<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA + rowb, segB + rowb, k, nvalid);
+        if (k == nvalid) {          // warp-uniform: a warp inside one row pair stores one segment (no per-chunk choice of base)
+            convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
+            store_row_rgb<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA, nvalid);
+            convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
+            store_row_rgb<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA + rowb, nvalid);
+        } else {
+            convert_row<S420, SWAP, BPP, false>(y0, cr, cg, cb, ow);
+            store_row_rgb2<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA, segB, k, nvalid);
+            convert_row<S420, SWAP, BPP, false>(y1, cr, cg, cb, ow);
+            store_row_rgb2<BPP, false>(reinterpret_cast<uint4 *>(out0), lane, ow, segA + rowb, segB + rowb, k, nvalid);
+        }
         rpA += qs;
         uA += rs;
         if (uA >= upr) { uA -= upr; rpA++; }
@@ -1456,8 +1463,8 @@ bool convert_tma_auto(const ConvertArgs &a)
     };
     const int upr = a.w / 16, lanes_row = ((upr + 31) / 32) * 32;
     // YUV420P whose rows leave more than a tenth of the row-pair form's lanes idle, or whose chroma rows that form cannot
-    // describe (width % 32 != 0): the flat form -- 0.90-0.92 of the copy rate at every width measured (PAL 0.83 -> 0.92, 1280x720
-    // 0.87 -> 0.92, 640x480 / 800x600 / 1600x900 0.83 -> 0.90), where the row-pair form reaches 0.96-0.99 on full warps
+    // describe (width % 32 != 0): the flat form -- 0.92-0.95 of the copy rate at every width measured (PAL 0.83 -> 0.92, 1280x720
+    // 0.87 -> 0.95, 640x480 / 1600x900 0.83 -> 0.93 / 0.94), where the row-pair form reaches 0.96-0.99 on full warps
     // (1920, 2560, 3840).  $ACGPU_TMA_FLAT: 0 never, 1 (default) that rule, 2 every width it can take.
     static const int flat_mode = [] { const char *e = getenv("ACGPU_TMA_FLAT"); return e ? atoi(e) : 1; }();
     if (a.srcfmt == IMG_YUV420P && (enabled & 1) && flat_mode && upr >= 32 && (uint64_t)upr * (uint64_t)(a.h / 2) < 0x7FFFFFFFu
