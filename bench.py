@@ -433,7 +433,7 @@ def measure(ac, dc, args, name, steps, warmup, do_e2e=True, do_cpu=True, clocks=
                            "h2d_gbs_concurrent": round(eb * sfb / t_both / 1e9, 2), "d2h_gbs_concurrent": round(eb * dfb / t_both / 1e9, 2),
                            "how": "per rank: the same source and result bytes as two concurrent pinned copies (H2D stream + D2H "
                                   "stream), every rank at once behind a barrier, max over ranks"},
-               "note": "through the host-buffer C-ABI call on pinned host buffers (3-slot upload / kernels / download pipeline); wall "
+               "note": "through the host-buffer C-ABI call on pinned host buffers (4-slot upload / kernels / download pipeline); wall "
                        "clock around the synchronous call, max over ranks"}
         hs.free(); hd.free()
     lib.acgpu_stream_destroy(stream)

@@ -239,7 +239,7 @@ int acgpu_chain_output(ImageFormat fmt, int width, int height, const acgpu_chain
 int acgpu_chain_batch(const uint8_t *src, ImageFormat fmt, int width, int height, size_t src_frame_pitch,
                       uint8_t *dest, size_t dest_frame_pitch, const acgpu_chain_op *ops, int nops, int nframes,
                       acgpu_stream_t stream);
-/* Host frames, tightly packed one after the other (best: acgpu_host_alloc memory): chunks of frames go through a three-slot
+/* Host frames, tightly packed one after the other (best: acgpu_host_alloc memory): chunks of frames go through a four-slot
  * upload / chain / download pipeline; returns after everything has landed in dest_frames.  The _multi form cuts the run
  * into one contiguous block per device like acgpu_imgconvert_frames_host_multi. */
 int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
