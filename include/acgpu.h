@@ -240,8 +240,8 @@ int acgpu_chain_batch(const uint8_t *src, ImageFormat fmt, int width, int height
                       uint8_t *dest, size_t dest_frame_pitch, const acgpu_chain_op *ops, int nops, int nframes,
                       acgpu_stream_t stream);
 /* Host frames, tightly packed one after the other (best: acgpu_host_alloc memory): chunks of frames go through a four-slot
- * upload / chain / download pipeline; returns after everything has landed in dest_frames.  The _multi form cuts the run
- * into one contiguous block per device like acgpu_imgconvert_frames_host_multi. */
+ * upload / chain / download pipeline; returns after everything has landed in dest_frames.  The _multi form shares the run
+ * out among the devices in grains of frames, like acgpu_imgconvert_frames_host_multi. */
 int acgpu_chain_frames_host(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
                             const acgpu_chain_op *ops, int nops, int nframes);
 int acgpu_chain_frames_host_multi(const uint8_t *src_frames, ImageFormat fmt, int width, int height, uint8_t *dest_frames,
