@@ -51,3 +51,57 @@ def test_reduced_forms_equal_literal_forms():
         subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "transcode-tcforge_b200", "csrc"), "-o", exe, src], check=True)
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0 and out.stdout.strip() == "0", out.stdout
+
+
+DIV_PROG = r'''
+#include "acgpu_internal.h"
+#include <cstdio>
+#include <cstdint>
+#include <random>
+// The kernels' division: q = umulhi(x, m) >> s, one compare fixes an estimate that is one too small (FastDiv::divmod).
+static bool check(uint32_t d, uint32_t x)
+{
+    const acgpu::FastDiv f = acgpu::make_fastdiv(d);
+    uint32_t q = (uint32_t)(((uint64_t)x * f.m) >> 32) >> f.s, r = x - q * d;
+    if (r >= d) { q++; r -= d; }
+    return q == x / d && r == x % d;
+}
+int main()
+{
+    std::mt19937_64 rng(20261019);
+    long bad = 0;
+    const uint32_t edge[] = {0u, 1u, 2u, 15u, 16u, 17u, 0x7FFFFFFFu, 0x80000000u, 0x80000001u, 0xFFFFFFF0u, 0xFFFFFFFFu};
+    for (uint32_t d = 1; d <= 70000; d++) {
+        for (uint32_t x : edge) bad += !check(d, x);
+        for (uint32_t k : {d - 1, d, d + 1, 2 * d - 1, 2 * d, 0xFFFFFFFFu / d * d, 0xFFFFFFFFu / d * d - 1}) bad += !check(d, k);
+        for (int i = 0; i < 8; i++) bad += !check(d, (uint32_t)rng());
+    }
+    for (int i = 0; i < 2000000; i++) {
+        uint32_t d = (uint32_t)rng();
+        if (!d) d = 1;
+        bad += !check(d, (uint32_t)rng());
+        bad += !check(d, d - 1) + !check(d, d) + !check(d, 0xFFFFFFFFu);
+    }
+    for (int s = 0; s < 32; s++) for (int o = -1; o <= 1; o++) {       // powers of two and their neighbours
+        const uint32_t d = (1u << s) + (uint32_t)o;
+        if (!d) continue;
+        for (int i = 0; i < 1000; i++) bad += !check(d, (uint32_t)rng());
+        for (uint32_t x : edge) bad += !check(d, x);
+    }
+    printf("%ld\n", bad);
+    return bad != 0;
+}
+'''
+
+
+def test_multiply_high_division_is_exact():
+    """FastDiv (acgpu_internal.h): the row / frame indices of the window copy and antialias kernels come from a
+    multiply-high with a host-made reciprocal instead of a division; exact for every 32-bit dividend."""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        open(src, "w").write(DIV_PROG)
+        exe = os.path.join(d, "t")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "transcode-tcforge_b200", "csrc"),
+                        "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", "-o", exe, src], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0 and out.stdout.strip() == "0", out.stdout
