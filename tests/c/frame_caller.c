@@ -7,6 +7,8 @@
  * The ONLY change from the reference is the allocator: tc_bufalloc / tc_buffree are defined as acgpu_bufalloc /
  * acgpu_buffree, the two-line patch INTEGRATION.md proposes for libtcutil/memutils.h.  Every legacy call on such a frame
  * then takes the page-locked path.  A third buffer shows the other route: an existing malloc'ed frame registered once.
+ * Last, a segment of the frame ring -- four frames, each in its own buffers -- goes through ONE frame-list chain call in
+ * place, as do_process_frame works on ptr->video_buf (-I 5 -G 0.8: src/video_trans.c:267-277, 390-396).
  * Prints the pointer kind of each buffer and digests of the results; tests/test_frame_plumbing.py checks both.
  */
 #include <stdio.h>
@@ -99,6 +101,30 @@ int main(int argc, char **argv)
     free(plain);
     tc_buffree(f.internal_video_buf_0);
     tc_buffree(f.internal_video_buf_1);
+
+    /* a segment of the frame ring through one chain call: every frame has buffers of its own, results replace the frames */
+    {
+        enum { RING = 4 };
+        frame_t ring[RING];
+        const uint8_t *in[RING];
+        uint8_t *out[RING];
+        acgpu_chain_op ops[2];
+        int i;
+        memset(ops, 0, sizeof(ops));
+        ops[0].kind = ACGPU_CHAIN_DEINTERLACE; ops[0].p[0] = 5;
+        ops[1].kind = ACGPU_CHAIN_GAMMA; ops[1].d[0] = 0.8;
+        for (i = 0; i < RING; i++) {
+            if (!frame_alloc(&ring[i], w, h)) return 1;
+            fill(ring[i].video_buf, (size_t)w * h * 3 / 2, 10 + (unsigned)i);
+            in[i] = out[i] = ring[i].video_buf;
+        }
+        if (!acgpu_chain_frame_list_host(in, IMG_YUV420P, w, h, out, ops, 2, RING)) { fprintf(stderr, "%s\n", acgpu_last_error()); return 1; }
+        for (i = 0; i < RING; i++) {
+            printf("ring_%d %016llx\n", i, fnv(ring[i].video_buf, (size_t)w * h * 3 / 2));
+            tc_buffree(ring[i].internal_video_buf_0);
+            tc_buffree(ring[i].internal_video_buf_1);
+        }
+    }
     tcv_free(tcv);
     return 0;
 }

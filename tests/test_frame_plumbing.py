@@ -30,7 +30,8 @@ def build():
 def test_frame_caller_compiles_and_links():
     build()
     out = subprocess.run(["nm", "-D", "--undefined-only", EXE], capture_output=True, text=True, check=True).stdout
-    assert {"acgpu_bufalloc", "acgpu_buffree", "acgpu_host_register", "ac_imgconvert", "tcv_flip_v", "tcv_convert"} <= \
+    assert {"acgpu_bufalloc", "acgpu_buffree", "acgpu_host_register", "ac_imgconvert", "tcv_flip_v", "tcv_convert",
+            "acgpu_chain_frame_list_host"} <= \
         {l.split()[-1] for l in out.splitlines()}
 
 
@@ -70,3 +71,9 @@ def test_frame_buffers_are_page_locked_and_calls_match_the_checker(size):
     # by now buffer 0 holds the flipped RGB frame: its first w*h*3/2 bytes are what the last conversion reads as YUV420P
     _, bgr = chk.convert(flipped[: F.frame_bytes(F.IMG_YUV420P, w, h)], F.IMG_YUV420P, F.IMG_BGR24, w, h, pad=0)
     assert got["yuv420p_bgr24"] == fnv(bgr)
+    # the ring segment: four frames in buffers of their own, one acgpu_chain_frame_list_host call, in place (-I 5 -G 0.8)
+    from chain_ref import DEINTERLACE, GAMMA, ref_chain
+    for i in range(4):
+        frame = lcg_bytes(F.frame_bytes(F.IMG_YUV420P, w, h), 10 + i)
+        want, of, ow, oh = ref_chain(tcv, chk, frame, F.IMG_YUV420P, w, h, [(DEINTERLACE, 5), (GAMMA, 0.8)])
+        assert (of, ow, oh) == (F.IMG_YUV420P, w, h) and got["ring_%d" % i] == fnv(want), i
