@@ -266,7 +266,10 @@ public:
     // copies n bytes with the helpers' aid; the caller takes the last piece itself and returns when all are done
     void copy(uint8_t *d, const uint8_t *s, size_t n, bool parallel)
     {
-        constexpr size_t kPiece = 256u << 10;
+        // smallest piece worth handing to a helper ($ACGPU_COPY_PIECE_KB).  64 KB: a 1080p chroma plane (518 KB) and the last,
+        // partial slot of a plane are shared out too -- with 256 KB they were copied by the caller alone and a lone caller on
+        // pageable 1080p frames made 1.9-2.5 k conversions/s instead of 3.0 k (profiles/r2_experiments.md section 5)
+        static const size_t kPiece = [] { const char *e = getenv("ACGPU_COPY_PIECE_KB"); const int v = e ? atoi(e) : 64; return (size_t)(v < 16 ? 16 : v) << 10; }();
         if (!parallel || nthreads == 0 || n < 2 * kPiece) { memcpy(d, s, n); return; }
         const int pieces = (int)std::min<size_t>((size_t)nthreads + 1, n / kPiece);
         const size_t each = (n / (size_t)pieces + 63) & ~(size_t)63;
